@@ -1,0 +1,46 @@
+// index_impl.h -- private layout of the opaque icd_index handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/icdrag.h"
+
+namespace icd {
+
+struct DeviceBuf {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+};
+
+}  // namespace icd
+
+struct icd_index {
+  int dim = 0, device = 0, flags = 0;
+  int64_t cap = 0, n = 0;
+  bool adopted = false;
+  // HBM layout: row-major [n, dim] bf16 table (the scanned copy), optional fp32 master,
+  // one level byte per row
+  void* table = nullptr;
+  float* master = nullptr;
+  uint8_t* levels = nullptr;
+  // TMA descriptor of `table` for the tensor scan (CUtensorMap is 128 bytes, 64-byte aligned)
+  alignas(128) unsigned char tmap[128];
+  bool map_valid = false;
+  int64_t map_rows = 0;
+  // workspace
+  icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage;
+  // stage timing (scan, merge, finalise)
+  cudaEvent_t ev[4];
+  bool timing = false, timing_pending = false;
+  int last_launches = 0;
+};
+
+namespace icd {
+int index_stage_queries(icd_index* x, const void* q, int q_dtype, int B, cudaStream_t st);
+int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, int64_t row_offset,
+                        float* d_score, float* d_raw, int64_t* d_id, uint8_t* d_level,
+                        bool q_exact_bf16, cudaStream_t st);
+int copy_out(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
+}  // namespace icd

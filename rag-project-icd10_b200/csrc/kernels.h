@@ -1,0 +1,89 @@
+// kernels.h -- host-side launch interfaces between the translation units of libicdrag.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace icd {
+
+// ---- scan_stream.cu
+struct StreamScanArgs {
+  const void* table;      // [n_rows, dim] bf16 or fp32 (f32rows)
+  const uint8_t* levels;  // [n_rows]
+  int64_t n_rows;
+  int dim;
+  bool f32rows;
+  const float* q;  // [nq, dim] fp32, first query of this pass
+  int nq;          // queries in this pass (<= stream_scan_max_queries)
+  int q0;          // index of the first query of this pass within the batch (partial buffer row)
+  int k;
+  int weight_pre;
+  float* part_score;  // [B, P, k]
+  int* part_id;       // [B, P, k] local row, -1 = empty
+  int P;              // partial lists per query == grid size
+};
+int stream_scan_grid();
+int stream_scan_max_queries(bool f32rows, int dim);
+int launch_stream_scan(const StreamScanArgs& a, cudaStream_t st);
+
+// ---- scan_tc.cu (tcgen05 / TMEM / TMA)
+struct TensorScanArgs {
+  const void* table;      // [n_rows, dim] bf16, 16-byte aligned rows
+  const uint8_t* levels;  // [n_rows]
+  int64_t n_rows;
+  int dim;                 // multiple of 64, <= 768
+  const void* q_bf16;      // [B, dim] bf16 device
+  int B;
+  int k;
+  int weight_pre;
+  float* part_score;  // [B, P, k]
+  int* part_id;       // [B, P, k]
+  int P;              // partial lists per query the buffers were sized for (>= groups used)
+  int* groups_used;   // out: partial lists actually written per query
+};
+int tensor_scan_max_partials();
+bool tensor_scan_supported(int dim, int k);
+int launch_tensor_scan(const TensorScanArgs& a, const void* tensor_map_owner, cudaStream_t st);
+// builds (or rebuilds) the TMA descriptor of the table; owner is an opaque 128-byte aligned blob
+int tensor_scan_make_map(void* map128, const void* table, int64_t n_rows, int dim);
+
+// ---- topk_merge.cu
+struct MergeArgs {
+  const float* part_score;  // [B, P, k_in] each list sorted (score desc, id asc); -inf/-1 padded
+  const int* part_id;       // [B, P, k_in] local rows
+  int B, P, k_in;
+  int k_out;                 // <= k_in
+  float* out_score;          // [B, k_out]
+  int64_t* out_id;           // [B, k_out] local row + row_offset, -1 = empty
+  int64_t row_offset;
+};
+int launch_merge(const MergeArgs& a, cudaStream_t st);
+
+struct FinaliseArgs {
+  // candidate lists from S sources (S = 1 locally, S = world after a shard exchange),
+  // laid out [S][B][kcp]; total S*kcp <= 1024
+  const float* cand_score;
+  const int64_t* cand_id;       // global ids, -1 = empty
+  const uint8_t* cand_level;    // [S][B][kcp] or null -> levels[id - row_offset]
+  int S, B, kcp, k;
+  int64_t row_offset;  // global id - row_offset = local row
+  int64_t n_local;
+  // exact rescoring (optional: q_f32 == nullptr keeps cand_score). Canonical fp32 order of
+  // scan_stream.cu so both scan paths return bit-identical scores.
+  const float* q_f32;  // [B, dim]
+  const void* rows;    // bf16 table or fp32 master of the local shard
+  bool f32rows;
+  int dim;
+  const uint8_t* levels;  // local levels
+  int weight_mode;        // ICD_WEIGHT_*
+  float* out_score;    // [B, k] may be null
+  float* out_raw;      // [B, k] may be null
+  int64_t* out_id;     // [B, k] may be null
+  uint8_t* out_level;  // [B, k] may be null
+};
+int launch_finalise(const FinaliseArgs& a, cudaStream_t st);
+
+// elementwise helpers
+int launch_f32_to_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t st);
+int launch_bf16_to_f32(const void* in_bf16, float* out, int64_t n, cudaStream_t st);
+
+}  // namespace icd

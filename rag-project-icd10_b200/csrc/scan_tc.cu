@@ -1,0 +1,358 @@
+// scan_tc.cu -- tensor-core exact inner-product scan with fused per-query top-k (sm_100a).
+//
+// Replaces the brute-force FLAT/IP search inside MilvusClient.search (reference call site
+// services/milvus_service.py:280-285) for batched queries.  scores = Q[B,dim] * C[N,dim]^T is
+// never materialised:
+//
+//   * a CTA owns one tile of 128 queries for its whole life.  The tile lives in TENSOR MEMORY
+//     as the MMA A operand (128 lanes x dim/2 columns of packed bf16, <= 384 columns), so
+//     shared memory is free for streaming the table.
+//   * table rows stream HBM -> shared memory through TMA (64 rows x 64 bf16 boxes, 128-byte
+//     swizzle) in a ring of mbarrier-tracked stages and are the MMA B operand (K-major).
+//   * tcgen05.mma (M=128 queries, N=64 rows, K=16) accumulates a 128x64 fp32 tile in TMEM;
+//     two accumulator buffers let the MMA of tile t+1 overlap the epilogue of tile t.
+//   * epilogue: thread == TMEM lane == query.  It reads its 64 scores with tcgen05.ld,
+//     compares against its private k-th best (a register) and only on the rare hit inserts
+//     into its private sorted list in shared memory.  Level weights (ICD_WEIGHT_PRE) are
+//     applied here.
+//   * grid = G row groups x T query tiles; each CTA writes one sorted list per query to the
+//     partial buffer [B, G, k] that topk_merge.cu reduces.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+//
+// Roofline: HBM for B <~ 200 (one pass over the table per launch), bf16 tensor pipe above.
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace icd {
+namespace {
+
+constexpr int BM = 128;  // queries per CTA
+constexpr int BN = 64;   // table rows per accumulator tile
+constexpr int BK = 64;   // bf16 per TMA box row (128 bytes)
+constexpr int kStageBytes = BN * BK * 2;  // 8 KiB
+constexpr int kMaxStages = 24;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccCol0 = 384;  // accumulators live behind the query tile
+constexpr int kSmemLimit = 227 * 1024;
+
+struct ScanParams {
+  const uint8_t* levels;
+  const __nv_bfloat16* q;  // [B, dim]
+  float* part_score;       // [B, G, kc]
+  int* part_id;
+  int64_t n_rows;
+  int dim, nkb;  // nkb = dim / 64
+  int B, kc, weight_pre;
+  int G, T;      // row groups, query tiles in this launch
+  int qt0;       // first query tile of this launch
+  int nst;       // pipeline stages
+};
+
+__device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, int id) {
+  // private sorted list, entry j of this thread at [j * BM]; precondition s > ls[(kc-1)*BM]
+  int j = kc - 1;
+  while (j > 0 && ls[(j - 1) * BM] < s) {
+    ls[j * BM] = ls[(j - 1) * BM];
+    li[j * BM] = li[(j - 1) * BM];
+    --j;
+  }
+  ls[j * BM] = s;
+  li[j * BM] = id;
+  return ls[(kc - 1) * BM];
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x / p.T;
+  const int qt = p.qt0 + blockIdx.x % p.T;
+
+  // shared memory carve-up
+  unsigned char* stage_base = smem;                                           // nst * 8 KiB, 1024-aligned
+  float* list_s = reinterpret_cast<float*>(smem + (size_t)p.nst * kStageBytes);  // [kc][BM]
+  int* list_i = reinterpret_cast<int*>(list_s + (size_t)p.kc * BM);           // [kc][BM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + (size_t)p.kc * BM);
+  uint64_t* full_bar = bars;                    // [nst]
+  uint64_t* empty_bar = bars + kMaxStages;      // [nst]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  // row tiles of this group
+  const int64_t total_tiles = (p.n_rows + BN - 1) / BN;
+  const int64_t t0 = total_tiles * g / p.G;
+  const int64_t t1 = total_tiles * (g + 1) / p.G;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap);
+    for (int s = 0; s < p.nst; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), 4);  // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_holder), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // epilogue threads: lane quarter and query of this thread
+  const int ep_lane = 32 * (warp & 3) + lane;  // TMEM lane == query within the tile
+  const int query = qt * BM + ep_lane;
+  float* my_s = list_s + ep_lane;
+  int* my_i = list_i + ep_lane;
+
+  if (warp >= 2) {
+    // private list init
+    for (int j = 0; j < p.kc; ++j) {
+      my_s[j * BM] = -INFINITY;
+      my_i[j * BM] = -1;
+    }
+    // query tile -> TMEM: lane = query, 32-bit column c holds elements (2c, 2c+1)
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint4* qrow = reinterpret_cast<const uint4*>(p.q + (size_t)query * p.dim);
+    for (int c16 = 0; c16 < p.dim / 32; ++c16) {  // 16 columns = 32 bf16 = 4 x uint4
+      uint32_t r[16];
+      if (query < p.B) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 t = qrow[c16 * 4 + v];
+          r[4 * v + 0] = t.x;
+          r[4 * v + 1] = t.y;
+          r[4 * v + 2] = t.z;
+          r[4 * v + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) r[v] = 0u;
+      }
+      ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(c16 * 16), r);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = t0; t < t1; ++t) {
+        const int row = (int)(t * BN);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+          ptx::mbar_expect_tx(fb, kStageBytes);
+          ptx::tma_load_2d(ptx::smem_u32(stage_base + (size_t)stage * kStageBytes), &tmap, fb, kb * BK, row);
+          if (++stage == p.nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int64_t t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(kAccCol0 + buf * BN);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(stage_base + (size_t)stage * kStageBytes);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            const uint64_t bdesc = ptx::make_desc_k128(sa + k4 * 32);
+            const uint32_t a_tmem = tmem_base + (uint32_t)((kb * (BK / 16) + k4) * 8);
+            ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | k4) ? 1u : 0u);
+          }
+          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // frees the stage when the MMAs retire
+          if (++stage == p.nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));  // accumulator tile complete
+      }
+    }
+  } else {
+    // ===================== epilogue: fused top-k =====================
+    const bool live = query < p.B;
+    float thr = live ? -INFINITY : INFINITY;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    int it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t r[BN];
+      const uint32_t acc = lane_addr + (uint32_t)(kAccCol0 + buf * BN);
+      ptx::tmem_ld_32x32b_x32(acc, r);
+      ptx::tmem_ld_32x32b_x32(acc + 32, r + 32);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));  // accumulator may be overwritten
+
+      const int64_t row0 = t * BN;
+      const int valid = (int)min((int64_t)BN, p.n_rows - row0);
+      if (p.weight_pre) {
+        // level bytes of the 64 rows of this tile (same for every thread: broadcast loads)
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const uint8_t lv = (c < valid) ? p.levels[row0 + c] : (uint8_t)2;
+          r[c] = __float_as_uint(__uint_as_float(r[c]) * level_weight_f(lv));
+        }
+      }
+      float m = __uint_as_float(r[0]);
+#pragma unroll
+      for (int c = 1; c < BN; ++c) m = fmaxf(m, __uint_as_float(r[c]));
+      if (m > thr) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {
+          const float s = __uint_as_float(r[c]);
+          if (s > thr && c < valid) thr = list_insert(my_s, my_i, p.kc, s, (int)(row0 + c));
+        }
+      }
+    }
+    // one sorted list per (query, group)
+    if (live) {
+      float* out_s = p.part_score + ((size_t)query * p.G + g) * p.kc;
+      int* out_i = p.part_id + ((size_t)query * p.G + g) * p.kc;
+      for (int j = 0; j < p.kc; ++j) {
+        out_s[j] = my_s[j * BM];
+        out_i[j] = my_i[j * BM];
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+size_t smem_bytes(int nst, int kc) {
+  return (size_t)nst * kStageBytes + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
+}
+
+}  // namespace
+
+int make_tmap_bf16_2d(void* map128, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols, bool swizzle128) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ICD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+    if (!sym || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return ICD_E_CUDA;
+    }
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+    return ICD_E_CUDA;
+  }
+  return ICD_OK;
+}
+
+int tensor_scan_max_partials() { return kSMs; }
+
+bool tensor_scan_supported(int dim, int k) {
+  return dim % BK == 0 && dim >= BK && dim <= 768 && k >= 1 && k <= ICD_MAX_K;
+}
+
+int tensor_scan_make_map(void* map128, const void* table, int64_t n_rows, int dim) {
+  return make_tmap_bf16_2d(map128, table, (uint64_t)n_rows, (uint64_t)dim, BN, BK, true);
+}
+
+int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
+  if (!tensor_scan_supported(a.dim, a.k)) {
+    set_error("tensor scan: unsupported dim=%d k=%d", a.dim, a.k);
+    return ICD_E_UNSUPPORTED;
+  }
+  const int T_total = (a.B + BM - 1) / BM;
+  const int64_t total_tiles = (a.n_rows + BN - 1) / BN;
+  const int T_launch = std::min(T_total, kSMs);
+  int G = std::max(1, kSMs / T_launch);
+  G = (int)std::min<int64_t>(G, total_tiles);
+  G = std::min(G, a.P);
+  *a.groups_used = G;
+
+  // pipeline depth from the shared memory left after the per-thread lists
+  int nst = kMaxStages;
+  while (nst > 2 && smem_bytes(nst, a.k) > (size_t)kSmemLimit) --nst;
+  if (smem_bytes(nst, a.k) > (size_t)kSmemLimit) {
+    set_error("tensor scan: k=%d does not fit shared memory", a.k);
+    return ICD_E_UNSUPPORTED;
+  }
+  const size_t smem = smem_bytes(nst, a.k);
+  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CUtensorMap tmap;
+  memcpy(&tmap, map128, sizeof(CUtensorMap));
+  for (int qt0 = 0; qt0 < T_total; qt0 += T_launch) {
+    ScanParams p{};
+    p.levels = a.levels;
+    p.q = reinterpret_cast<const __nv_bfloat16*>(a.q_bf16);
+    p.part_score = a.part_score;
+    p.part_id = a.part_id;
+    p.n_rows = a.n_rows;
+    p.dim = a.dim;
+    p.nkb = a.dim / BK;
+    p.B = a.B;
+    p.kc = a.k;
+    p.weight_pre = a.weight_pre;
+    p.G = G;
+    p.T = std::min(T_launch, T_total - qt0);
+    p.qt0 = qt0;
+    p.nst = nst;
+    scan_tc_kernel<<<G * p.T, kThreads, smem, st>>>(tmap, p);
+    count_launch();
+    ICD_CUDA(cudaGetLastError());
+  }
+  return ICD_OK;
+}
+
+}  // namespace icd

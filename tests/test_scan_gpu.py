@@ -1,0 +1,212 @@
+"""GPU parity of the exact top-k scan (both kernels) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from oracle import search as osearch
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+
+
+def _corpus(n, dim, seed, bf16=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return osearch.bf16_round(x) if bf16 else x
+
+
+def _levels(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.choice(np.array([1, 2, 3], np.uint8), size=n, p=[0.1243, 0.2991, 0.5766]).astype(np.uint8)
+
+
+def _index(pkg, corpus, levels, keep_f32=False):
+    from importlib import import_module
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(corpus.shape[1], device=0, keep_f32=keep_f32)
+    idx.append(corpus, levels)
+    assert len(idx) == corpus.shape[0]
+    return idx
+
+
+def _exact_of(corpus, q):
+    return lambda b, ids: corpus[np.asarray(ids)] @ q[b]
+
+
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("n,B,k", [(5000, 1, 10), (5000, 3, 5), (40474, 7, 10), (20000, 130, 10),
+                                    (3001, 257, 1), (9999, 33, 100), (64, 2, 10), (1, 1, 10), (7, 5, 10)])
+def test_scan_matches_oracle(pkg, native, path, n, B, k):
+    dim = 768
+    corpus = _corpus(n, dim, seed=n + B)
+    levels = _levels(n, seed=n)
+    q = _corpus(B, dim, seed=999 + B)
+    idx = _index(pkg, corpus, levels)
+    score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=path)
+    ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+    kk = min(k, n)
+    assert np.all(ids[:, kk:] == -1) and np.all(np.isneginf(raw[:, kk:]))
+    swaps = check_topk(ids[:, :kk], raw[:, :kk], ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    assert np.array_equal(score, raw)
+    assert swaps <= max(1, B * kk // 50), f"{swaps} tie swaps out of {B * kk}"
+    idx.close()
+
+
+def test_stream_and_tensor_paths_agree_bitwise(pkg, native):
+    """Both scan kernels feed the same canonical fp32 rescoring, so scores agree bit for bit."""
+    corpus = _corpus(30000, 768, seed=5)
+    levels = _levels(30000, seed=6)
+    q = _corpus(64, 768, seed=7)
+    idx = _index(pkg, corpus, levels)
+    s1, r1, i1 = idx.search(q, 10, weight_mode=native.WEIGHT_RERANK, path=native.PATH_STREAM)
+    s2, r2, i2 = idx.search(q, 10, weight_mode=native.WEIGHT_RERANK, path=native.PATH_TENSOR)
+    assert np.array_equal(i1, i2)
+    assert np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
+    assert np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    idx.close()
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_rerank_matches_reference_rule(pkg, native, path):
+    """ICD_WEIGHT_RERANK == milvus_service.py:290-314: raw top-k, score*w(level), stable re-sort."""
+    n, B, k = 40474, 16, 10
+    corpus = _corpus(n, 768, seed=11)
+    levels = _levels(n, seed=12)
+    q = _corpus(B, 768, seed=13)
+    idx = _index(pkg, corpus, levels)
+    score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_RERANK, path=path)
+    ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+    for b in range(B):
+        assert set(ids[b].tolist()) == set(ref_i[b].tolist())
+        # re-rank the kernel's own raw list with the oracle rule: must reproduce the kernel's order
+        order0 = np.lexsort((ids[b], -raw[b].astype(np.float64)))
+        order, weighted = osearch.rerank(raw[b][order0], levels[ids[b][order0]])
+        assert [int(ids[b][order0][j]) for j in order] == ids[b].tolist()
+        np.testing.assert_allclose(score[b], np.array([weighted[j] for j in order], np.float32), rtol=0, atol=1e-7)
+    idx.close()
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_pre_weighting_selects_on_weighted_score(pkg, native, path):
+    n, B, k = 20000, 9, 10
+    corpus = _corpus(n, 768, seed=21)
+    levels = _levels(n, seed=22)
+    q = _corpus(B, 768, seed=23)
+    idx = _index(pkg, corpus, levels)
+    score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_PRE, path=path)
+    w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
+    full = (q @ corpus.T) * w[None, :]
+    for b in range(B):
+        ref = np.lexsort((np.arange(n), -full[b].astype(np.float64)))[:k]
+        got_w = full[b][ids[b]]
+        assert np.all(np.abs(got_w - full[b][ref]) <= 1e-3)
+        np.testing.assert_allclose(score[b], got_w, atol=2e-6)
+    idx.close()
+
+
+def test_fp32_master_search_is_exact_fp32(pkg, native):
+    """KEEP_F32 tables are searched like Milvus FLAT: fp32 rows, fp32 query, fp32 accumulate."""
+    n, k = 40474, 10
+    corpus = _corpus(n, 768, seed=31, bf16=False)
+    q = _corpus(4, 768, seed=32, bf16=False)
+    idx = _index(pkg, corpus, _levels(n, 33), keep_f32=True)
+    for path in (native.PATH_AUTO, native.PATH_TENSOR):
+        score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=path)
+        ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+        check_topk(ids, raw, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    got = idx.read(100, 5)
+    assert np.array_equal(got, corpus[100:105])
+    idx.close()
+
+
+def test_device_tensors_and_adopt(pkg, native):
+    import torch
+    n, B, k = 50000, 200, 10
+    corpus = _corpus(n, 768, seed=41)
+    levels = _levels(n, 42)
+    q = _corpus(B, 768, seed=43)
+    t = torch.from_numpy(corpus).cuda().to(torch.bfloat16)
+    lv = torch.from_numpy(levels).cuda()
+    from importlib import import_module
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(768, device=0)
+    idx.adopt(t, lv)
+    qd = torch.from_numpy(q).cuda().to(torch.bfloat16)
+    score, raw, ids = idx.search(qd, k, weight_mode=native.WEIGHT_NONE)
+    torch.cuda.synchronize()
+    assert ids.is_cuda and raw.dtype == torch.float32
+    ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+    check_topk(ids.cpu().numpy(), raw.cpu().numpy(), ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    with pytest.raises(native.NativeError):
+        idx.append(corpus[:4], levels[:4])
+    idx.close()
+
+
+def test_append_grows_and_clear(pkg, native):
+    corpus = _corpus(5000, 768, seed=51)
+    levels = _levels(5000, 52)
+    from importlib import import_module
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(768, device=0, capacity=16)
+    for lo in range(0, 5000, 700):
+        idx.append(corpus[lo:lo + 700], levels[lo:lo + 700])
+    assert len(idx) == 5000
+    q = _corpus(2, 768, seed=53)
+    _, raw, ids = idx.search(q, 5, weight_mode=native.WEIGHT_NONE)
+    ref_s, ref_i = osearch.exact_topk(corpus, q, 5)
+    check_topk(ids, raw, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    idx.clear()
+    assert len(idx) == 0
+    _, raw, ids = idx.search(q, 5)
+    assert np.all(ids == -1)
+    idx.close()
+
+
+def test_small_dim_golden_vectors(pkg, native, golden_dir):
+    """The 8-d vectors of tests/golden/milvus_service_golden.json (reference-generated)."""
+    import json, os
+    g = json.load(open(os.path.join(golden_dir, "milvus_service_golden.json"), encoding="utf-8"))
+    vecs = np.asarray(g["vectors"], np.float32)
+    from importlib import import_module
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(vecs.shape[1], device=0, keep_f32=True)
+    idx.append(vecs, np.ones(len(vecs), np.uint8))
+    for s in g["searches"]:
+        q = np.asarray(s["query"], np.float32)
+        _, raw, ids = idx.search(q, s["top_k"], weight_mode=native.WEIGHT_NONE)
+        want = sorted(s["hits"], key=lambda h: -h["original_score"])
+        got_codes = [g["codes"][int(i)] for i in ids[0]]
+        assert sorted(got_codes) == sorted(h["code"] for h in want)
+        np.testing.assert_allclose(np.sort(raw[0])[::-1], [h["original_score"] for h in want], atol=1e-6)
+    idx.close()
+
+
+def test_full_size_properties(pkg, native):
+    """BASELINE-size property checks (no oracle pass over 10 M rows): planted neighbours are found,
+    results are sorted, and the two kernels agree."""
+    import torch
+    n, B, k, dim = 2_000_000, 256, 10, 768
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    t = torch.empty((n, dim), dtype=torch.bfloat16, device="cuda")
+    for lo in range(0, n, 250_000):
+        x = torch.randn((250_000, dim), generator=g, device="cuda")
+        t[lo:lo + 250_000] = torch.nn.functional.normalize(x, dim=1).to(torch.bfloat16)
+    lv = torch.randint(1, 4, (n,), device="cuda", dtype=torch.uint8, generator=g)
+    planted = torch.randint(0, n, (B,), device="cuda", generator=g)
+    q = torch.nn.functional.normalize(t[planted].float() + 0.3 / dim ** 0.5 * torch.randn((B, dim), device="cuda", generator=g), dim=1)
+    q = q.to(torch.bfloat16)
+    from importlib import import_module
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(dim, device=0)
+    idx.adopt(t, lv)
+    _, raw2, ids2 = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
+    _, raw1, ids1 = idx.search(q[:8], k, weight_mode=native.WEIGHT_NONE, path=native.PATH_STREAM)
+    torch.cuda.synchronize()
+    assert torch.equal(ids2[:, 0], planted)
+    assert torch.all(raw2[:, :-1] >= raw2[:, 1:])
+    assert torch.equal(ids1, ids2[:8]) and torch.equal(raw1, raw2[:8])
+    # checksum-style property: the k-th score bounds every other row (sampled)
+    sample = torch.randint(0, n, (4096,), device="cuda", generator=g)
+    s = q.float() @ t[sample].float().T
+    assert torch.all(s <= raw2[:, :1] + 1e-6)
+    idx.close()
