@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the retrieval hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libicdrag.so on B200)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle)
+
+Workload (config.workload): exact top-10 inner-product search of a batch of 1024 synthetic
+768-d bf16 queries over a synthetic 100 M x 768 bf16 corpus -- BASELINE.json configs[4].  The
+corpus is row-sharded over the N GPUs (strong scaling: total rows fixed, 100 M / N per GPU; at
+N = 1 the whole 153.6 GB table sits in one B200's 180 GB).  One "step" = one batch through the
+scan.  `value` is queries/s with queries and corpus resident in HBM; `e2e` is the same metric
+through the C ABI with HOST query/result buffers (H2D + D2H inside the timed region).
+
+The corpus (15x-1200x the 126 MB L2) is far larger than L2, so every step streams it from HBM:
+no L2 flush is needed between iterations (config.l2 says so).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIM = 768
+K_TOP = 10
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_corpus(torch, rows, device, seed):
+    """i.i.d. N(0,1) -> fp32 L2-normalise -> bf16 (the bf16 values ARE the corpus);
+    level bytes ~ Categorical(0.1243, 0.2991, 0.5766).  Built in 1 M-row chunks."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    table = torch.empty((rows, DIM), dtype=torch.bfloat16, device=device)
+    chunk = 1 << 20
+    for lo in range(0, rows, chunk):
+        n = min(chunk, rows - lo)
+        x = torch.randn((n, DIM), generator=g, device=device, dtype=torch.float32)
+        x = torch.nn.functional.normalize(x, dim=1)
+        table[lo:lo + n] = x.to(torch.bfloat16)
+        del x
+    u = torch.rand((rows,), generator=g, device=device)
+    levels = torch.full((rows,), 3, dtype=torch.uint8, device=device)
+    levels[u < 0.1243 + 0.2991] = 2
+    levels[u < 0.1243] = 1
+    return table, levels
+
+
+def make_queries(torch, batch, device, seed=999):
+    g = torch.Generator(device=device).manual_seed(seed)
+    q = torch.randn((batch, DIM), generator=g, device=device, dtype=torch.float32)
+    return torch.nn.functional.normalize(q, dim=1).to(torch.bfloat16)
+
+
+def cpu_sample(rows, batch, reps=1):
+    """The reference's CPU search path (Milvus FLAT/IP restated: oracle.search.exact_topk, fp32
+    numpy over all host threads) on a bounded sample of the workload."""
+    import numpy as np
+    from oracle import search as osearch
+    rng = np.random.default_rng(1234)
+    corpus = rng.standard_normal((rows, DIM), dtype=np.float32)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    corpus = osearch.bf16_round(corpus)
+    q = rng.standard_normal((batch, DIM), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    osearch.exact_topk(corpus[: rows // 8], q[:8], K_TOP)  # warm BLAS threads
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        osearch.exact_topk(corpus, q, K_TOP)
+    dt = (time.perf_counter() - t0) / reps
+    return dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (restated: numpy
+    fp32 exact IP + top-k; pymilvus/milvus-lite are not installable offline), host cores only."""
+    if rank != 0:
+        return
+    import torch
+    total_rows = args.rows
+    sample_rows, sample_batch = args.cpu_rows, args.cpu_batch
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_sample(sample_rows, sample_batch)
+        if i >= args.warmup:
+            times.append(dt)
+    dt = sum(times) / len(times)
+    # one step of the real workload = batch x total_rows; the sample is batch' x rows' of the same
+    # arithmetic, cost linear in rows x batch (exact scan): extrapolate linearly and say so.
+    qps = sample_batch / dt * (sample_rows / total_rows)
+    line = {
+        "impl": "reference", "metric": "top-10 cosine QPS (100M x 768)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3 * (total_rows / sample_rows) * (args.batch / sample_batch),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"exact top-{K_TOP} IP, {total_rows} x {DIM} corpus, batch {args.batch}",
+                   "rows": total_rows, "dim": DIM, "batch": args.batch, "k": K_TOP},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "torch_threads": torch.get_num_threads(),
+                         "sample": f"{sample_batch} queries x {sample_rows} rows per step (numpy fp32 GEMM + exact "
+                                   f"top-k, oracle/search.py), extrapolated linearly in rows to {total_rows}"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="total corpus rows over all GPUs")
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 stream, 2 tensor")
+    ap.add_argument("--exchange", type=int, default=1, help="multi-GPU candidate exchange: 0 NCCL all-gather, 1 peer stores")
+    ap.add_argument("--cpu-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-batch", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    native = importlib.import_module("rag-project-icd10_b200._native")
+    VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    native.require_gpu()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+
+    peaks = _peaks()
+    rows_total = args.rows
+    lo = rows_total * rank // world
+    hi = rows_total * (rank + 1) // world
+    rows_local = hi - lo
+    workload = f"exact top-{K_TOP} IP, {rows_total} x {DIM} bf16 corpus row-sharded over {world} GPU(s), batch {args.batch}"
+    try:
+        table, levels = make_corpus(torch, rows_local, dev, 1234 + rank)
+    except torch.OutOfMemoryError:
+        if world > 1:
+            raise
+        rows_total = rows_local = 10_000_000
+        lo, hi = 0, rows_total
+        workload = (f"exact top-{K_TOP} IP, {rows_total} x {DIM} bf16 corpus (configs[3]: 100 M rows did not fit this "
+                    f"GPU), batch {args.batch}")
+        torch.cuda.empty_cache()
+        table, levels = make_corpus(torch, rows_local, dev, 1234)
+    q_dev = make_queries(torch, args.batch, dev)
+    q_host = q_dev.cpu().pin_memory()
+
+    idx = VectorIndex(DIM, device=local_rank)
+    idx.adopt(table, levels)
+    idx.set_timing(True)
+    group = None
+    if world > 1:
+        ShardGroup = importlib.import_module("rag-project-icd10_b200.engine.shard").ShardGroup
+        group = ShardGroup(idx, row_offset=lo, rank=rank, world=world)
+
+    B, k = args.batch, K_TOP
+    o_score = torch.empty((B, k), dtype=torch.float32, device=dev)
+    o_raw = torch.empty((B, k), dtype=torch.float32, device=dev)
+    o_id = torch.empty((B, k), dtype=torch.int64, device=dev)
+    h_score = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    h_raw = torch.empty((B, k), dtype=torch.float32).pin_memory()
+    h_id = torch.empty((B, k), dtype=torch.int64).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        if group is not None:
+            group.search(q_dev, k, out=(o_score, o_raw, o_id), path=args.path, exchange=args.exchange,
+                         stream=stream.cuda_stream, sync=False)
+        else:
+            idx.search(q_dev, k, weight_mode=native.WEIGHT_RERANK, path=args.path, out=(o_score, o_raw, o_id),
+                       stream=stream.cuda_stream, sync=False)
+
+    def step_host():
+        if group is not None:
+            group.search(q_host, k, out=(h_score, h_raw, h_id), path=args.path, exchange=args.exchange,
+                         stream=stream.cuda_stream, sync=True)
+        else:
+            idx.search(q_host, k, weight_mode=native.WEIGHT_RERANK, path=args.path, out=(h_score, h_raw, h_id),
+                       stream=stream.cuda_stream, sync=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------ device-resident timing (value)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = native.lib().icd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_us = []
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = native.lib().icd_launch_count() - launches0
+    # scan-kernel time of the last step (events recorded by the library on the same stream)
+    tm = idx.last_timing()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, tm["scan_us"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, scan_us_max = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    qps = B / (ms_step * 1e-3)
+
+    # ------------------------------------------------ e2e through the C ABI with host buffers
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_qps = B / (float(t[0]) / args.steps)
+
+    # sanity: device and host paths return the same ids
+    step_device()
+    torch.cuda.synchronize(dev)
+    same = bool(torch.equal(o_id.cpu(), h_id))
+
+    if rank == 0:
+        flops = 2.0 * B * rows_local * DIM                     # per scan launch (per GPU)
+        bytes_alg = rows_local * DIM * 2 + B * DIM * 2 + B * k * 16
+        tensor_bound = flops / (peaks["bf16_tflops_sustained"] * 1e12) > bytes_alg / (peaks["hbm_gbs"] * 1e9)
+        scan_s = scan_us_max * 1e-6
+        if tensor_bound:
+            roof = {"bound": "tensor", "achieved": flops / scan_s / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s"}
+        else:
+            roof = {"bound": "hbm", "achieved": bytes_alg / scan_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["traffic"] = None
+        roof["kernel"] = "scan_tc_kernel" if tm["launches"] and B > 4 else "scan_stream_kernel"
+        roof["kernel_us"] = scan_us_max
+        roof["peak_source"] = peaks["source"] + (" (sustained)" if tensor_bound else "")
+        roof["hbm_gbs_of_scan"] = bytes_alg / scan_s / 1e9
+        line = {
+            "metric": "top-10 cosine QPS (100M x 768)", "value": qps, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "rows": rows_total, "rows_per_gpu": rows_local, "dim": DIM, "batch": B,
+                       "k": k, "weight_mode": "rerank", "l2": "corpus >> L2 (no flush needed)",
+                       "exchange": ("peer-store" if args.exchange else "nccl-allgather") if world > 1 else None},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 2,
+                    "d2h_bytes_per_step": B * k * 16},
+            "gpu_launches": int(launches), "launches_per_step": tm["launches"],
+            "roofline": roof, "clocks": clocks, "ids_match_host_device": same,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            dt = cpu_sample(args.cpu_rows, args.cpu_batch)
+            line["cpu_baseline"] = {
+                "value": args.cpu_batch / dt * (args.cpu_rows / rows_total), "unit": "queries/s",
+                "cores": os.cpu_count(), "kind": "port",
+                "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows (numpy fp32 exact IP + top-k, "
+                          f"oracle/search.py), extrapolated linearly in rows to {rows_total}"}
+        if not args.no_encoder:
+            try:
+                enc_bench = importlib.import_module("rag-project-icd10_b200.engine.encoder").bench_encoder
+                line["encoder"] = enc_bench(dev, peaks)
+            except Exception as e:  # encoder line is auxiliary; the headline must still print
+                line["encoder"] = {"error": repr(e)[:200]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,9 @@ extern "C" {
 /* element types of vectors crossing the ABI */
 #define ICD_F32 0
 #define ICD_BF16 1
+/* OR-ed into icd_encoder_forward's out_dtype: return the pooled mean without L2 normalisation
+ * (SentenceTransformer.encode(normalize_embeddings=False)) */
+#define ICD_OUT_NO_NORMALISE 0x100
 
 /* level weighting of MilvusService.search (services/milvus_service.py:290-314,550-558) */
 #define ICD_WEIGHT_RERANK 0 /* reference behaviour: raw top-k, then score*w(level), stable re-sort */

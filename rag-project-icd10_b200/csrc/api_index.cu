@@ -85,7 +85,7 @@ static int alloc_table(icd_index* x, int64_t cap) {
 // Writes [B, k] results into the given DEVICE buffers (any may be null).
 int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, int64_t row_offset,
                         float* d_score, float* d_raw, int64_t* d_id, uint8_t* d_level,
-                        bool q_exact_bf16, cudaStream_t st) {
+                        bool q_exact_bf16, const PushTargets* push, cudaStream_t st) {
   const int64_t n = x->n;
   const bool have_master = x->master != nullptr;
   const int weight_pre = weight_mode == ICD_WEIGHT_PRE ? 1 : 0;
@@ -207,6 +207,7 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
   f.out_raw = d_raw;
   f.out_id = d_id;
   f.out_level = d_level;
+  if (push) f.push = *push;
   ICD_TRY(launch_finalise(f, st));
   if (x->timing) cudaEventRecord(ev[3], st);
   x->last_launches = (int)(g_launches.load() - l0);
@@ -450,7 +451,7 @@ int icd_index_search(icd_index* x, const void* q, int q_dtype, int B, int k, int
     float* k_raw = (o_raw && is_device_ptr(o_raw)) ? o_raw : (o_raw ? d_raw : nullptr);
     int64_t* k_id = (o_id && is_device_ptr(o_id)) ? o_id : (o_id ? d_id : nullptr);
     ICD_TRY(index_search_device(x, nb, k, weight_mode, path, 0, k_score, k_raw, k_id, nullptr,
-                                q_dtype == ICD_BF16, st));
+                                q_dtype == ICD_BF16, nullptr, st));
     ICD_TRY(copy_out(o_score, k_score, (size_t)nb * k * 4, st));
     ICD_TRY(copy_out(o_raw, k_raw, (size_t)nb * k * 4, st));
     ICD_TRY(copy_out(o_id, k_id, (size_t)nb * k * 8, st));

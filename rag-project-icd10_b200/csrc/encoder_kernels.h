@@ -1,0 +1,38 @@
+// encoder_kernels.h -- launch interfaces of the BERT encoder kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace icd {
+
+enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2 };
+
+// ---- gemm_tc.cu : out[M,N] = epi(A[M,K] * W[N,K]^T + bias)
+struct GemmArgs {
+  const void* tmap_a;  // 128-byte CUtensorMap of A (box 128 x 64, SWIZZLE_128B)
+  const void* tmap_b;  // CUtensorMap of W (box 256 x 64, SWIZZLE_128B)
+  const float* bias;   // [N] fp32
+  const void* residual;  // [M,N] bf16 (EPI_BIAS_RESIDUAL) or null
+  void* out;             // [M,N] bf16
+  int M, N, K;
+  int epi;
+};
+int gemm_tile_n();
+int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
+int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K);
+int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K);
+
+// ---- encoder_kernels.cu
+// h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0])
+int launch_embed_ln(const int32_t* ids, int M, int S, const float* word, const float* pos, const float* type0,
+                    const float* gamma, const float* beta, float eps, void* out_bf16, cudaStream_t st);
+// out = LayerNorm(x) row-wise over 768 columns
+int launch_layernorm(const void* x_bf16, int M, const float* gamma, const float* beta, float eps, void* out_bf16,
+                     cudaStream_t st);
+// softmax(Q K^T / 8 + mask) V for every (sequence, head); qkv is [M, 2304] = [q | k | v]
+int launch_attention(const void* qkv_bf16, const int32_t* lens, int B, int S, void* ctx_bf16, cudaStream_t st);
+// masked mean over tokens + L2 normalise -> [B,768] (fp32 or bf16)
+int launch_pool_normalise(const void* h_bf16, const int32_t* lens, int B, int S, void* out, int out_dtype,
+                          cudaStream_t st);
+
+}  // namespace icd

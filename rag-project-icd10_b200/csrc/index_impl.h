@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/icdrag.h"
+#include "kernels.h"
 
 namespace icd {
 
@@ -41,6 +42,6 @@ namespace icd {
 int index_stage_queries(icd_index* x, const void* q, int q_dtype, int B, cudaStream_t st);
 int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, int64_t row_offset,
                         float* d_score, float* d_raw, int64_t* d_id, uint8_t* d_level,
-                        bool q_exact_bf16, cudaStream_t st);
+                        bool q_exact_bf16, const PushTargets* push, cudaStream_t st);
 int copy_out(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);
 }  // namespace icd

@@ -58,12 +58,23 @@ struct MergeArgs {
 };
 int launch_merge(const MergeArgs& a, cudaStream_t st);
 
+// fused exchange, producer side: per-peer destinations of this rank's (raw, id, level) block
+struct PushTargets {
+  int n;
+  float* raw[8];
+  int64_t* id[8];
+  uint8_t* level[8];
+  uint32_t* flag[8];  // [B] per peer; flag[b] = epoch published with system-scope release
+  uint32_t epoch;
+};
+
 struct FinaliseArgs {
   // candidate lists from S sources (S = 1 locally, S = world after a shard exchange),
   // laid out [S][B][kcp]; total S*kcp <= 1024
   const float* cand_score;
   const int64_t* cand_id;       // global ids, -1 = empty
   const uint8_t* cand_level;    // [S][B][kcp] or null -> levels[id - row_offset]
+  size_t src_stride_bytes;      // 0: arrays are dense [S][B][kcp]; else source s starts s*stride bytes later
   int S, B, kcp, k;
   int64_t row_offset;  // global id - row_offset = local row
   int64_t n_local;
@@ -79,6 +90,13 @@ struct FinaliseArgs {
   float* out_raw;      // [B, k] may be null
   int64_t* out_id;     // [B, k] may be null
   uint8_t* out_level;  // [B, k] may be null
+  // fused exchange, producer side: after its [k] block is written, CTA b also stores the
+  // (raw, id, level) block into every peer's receive slab over NVLink-mapped pointers and
+  // publishes flag[b] = epoch there (system-scope release).
+  PushTargets push;
+  // fused exchange, consumer side: CTA b waits for wait_flag[s][b] == epoch of every source
+  const uint32_t* wait_flag;  // [S][B] or null
+  uint32_t epoch;
 };
 int launch_finalise(const FinaliseArgs& a, cudaStream_t st);
 

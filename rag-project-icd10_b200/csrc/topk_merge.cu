@@ -123,18 +123,49 @@ finalise_kernel(FinaliseArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kc = a.S * a.kcp;
 
+  // 0. fused exchange, consumer side: the blocks of query b pushed by every peer must have landed
+  if (a.wait_flag) {
+    if (threadIdx.x < a.S) {
+      const uint32_t* f = a.src_stride_bytes
+                              ? reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(a.wait_flag) +
+                                                                  (size_t)threadIdx.x * a.src_stride_bytes) + b
+                              : a.wait_flag + (size_t)threadIdx.x * a.B + b;
+      uint32_t spins = 0;
+      while (true) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == a.epoch) break;
+        if (++spins > (1u << 26)) {
+          printf("icdrag: peer flag wait timed out (query %d source %d: have %u want %u)\n", b, threadIdx.x, v, a.epoch);
+          __trap();
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+  }
+
   // 1. gather candidates, exact rescoring, levels
   for (int c = warp; c < kc; c += kFinThreads / 32) {
     const int s = c / a.kcp, j = c % a.kcp;
-    const size_t src = ((size_t)s * a.B + b) * a.kcp + j;
-    const int64_t id = a.cand_id[src];
-    float raw = a.cand_score[src];
+    size_t src = ((size_t)s * a.B + b) * a.kcp + j;
+    const float* cs = a.cand_score;
+    const int64_t* ci = a.cand_id;
+    const uint8_t* cl = a.cand_level;
+    if (a.src_stride_bytes) {
+      src = (size_t)b * a.kcp + j;
+      cs = reinterpret_cast<const float*>(reinterpret_cast<const char*>(cs) + (size_t)s * a.src_stride_bytes);
+      ci = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(ci) + (size_t)s * a.src_stride_bytes);
+      if (cl) cl += (size_t)s * a.src_stride_bytes;
+    }
+    const int64_t id = ci[src];
+    float raw = cs[src];
     uint8_t lv = 0;
     if (id >= 0) {
       const int64_t local = id - a.row_offset;
       const bool is_local = local >= 0 && local < a.n_local;
-      if (a.cand_level)
-        lv = a.cand_level[src];
+      if (cl)
+        lv = cl[src];
       else if (is_local && a.levels)
         lv = a.levels[local];
       if (a.q_f32 && is_local) {
@@ -210,6 +241,20 @@ finalise_kernel(FinaliseArgs a) {
     if (a.out_raw) a.out_raw[dst] = o_raw;
     if (a.out_id) a.out_id[dst] = o_id;
     if (a.out_level) a.out_level[dst] = o_lv;
+    for (int pr = 0; pr < a.push.n; ++pr) {
+      a.push.raw[pr][dst] = o_raw;
+      a.push.id[pr][dst] = o_id;
+      a.push.level[pr][dst] = o_lv;
+    }
+  }
+  // fused exchange, producer side: publish this query's block to every peer
+  if (a.push.n > 0) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < a.push.n) {
+      uint32_t* f = a.push.flag[threadIdx.x] + b;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.push.epoch) : "memory");
+    }
   }
 }
 

@@ -1,0 +1,159 @@
+"""GPU parity of the BERT sentence encoder (tcgen05 GEMMs + fused epilogues + attention + pool)
+against the CPU oracle (HF BertModel fp32 -> masked mean -> L2 normalise), through the C ABI.
+Tolerance (BASELINE.json north_star): cosine >= 0.999 per sentence."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import encoder as oenc
+from oracle import text as otext
+from parity import COS_MIN, cosine_rows
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mods():
+    N = importlib.import_module("rag-project-icd10_b200._native")
+    E = importlib.import_module("rag-project-icd10_b200.engine.encoder")
+    W = importlib.import_module("rag-project-icd10_b200.engine.weights")
+    return N, E, W
+
+
+def _oracle_forward(state, layers, vocab, ids, lens):
+    import torch
+    from transformers import BertModel
+    model = BertModel(oenc.bert_config(layers, vocab, 512), add_pooling_layer=False)
+    model.load_state_dict(state, strict=False)
+    model.eval()
+    S = ids.shape[1]
+    mask = torch.from_numpy((np.arange(S)[None, :] < lens[:, None]).astype(np.int64))
+    with torch.no_grad():
+        h = model(input_ids=torch.from_numpy(ids.astype(np.int64)), attention_mask=mask).last_hidden_state
+        m = mask.unsqueeze(-1).float()
+        pooled = (h * m).sum(1) / m.sum(1).clamp(min=1e-9)
+        return torch.nn.functional.normalize(pooled, dim=1).numpy(), pooled.numpy(), h.numpy()
+
+
+@pytest.fixture(scope="module")
+def small():
+    N, E, W = _mods()
+    vocab, layers = 2000, 2
+    state = oenc.synthetic_state_dict(seed=11, num_layers=layers, vocab_size=vocab)
+    cfg = N.BertCfg(vocab_size=vocab, hidden=768, layers=layers, heads=12, intermediate=3072, max_position=512,
+                    type_vocab=2, ln_eps=1e-12)
+    eng = E.EncoderEngine(cfg=cfg, blob=W.pack_state_dict(state, cfg), tokenizer=object(), device=0, max_tokens=8192)
+    yield eng, state, layers, vocab
+    eng.close()
+
+
+@pytest.mark.parametrize("B,S", [(1, 1), (1, 7), (5, 24), (3, 64), (2, 128), (37, 33), (130, 16)])
+def test_forward_matches_oracle(small, B, S):
+    eng, state, layers, vocab = small
+    rng = np.random.default_rng(B * 1000 + S)
+    lens = rng.integers(1, S + 1, size=B).astype(np.int32)
+    lens[0] = S
+    ids = np.zeros((B, S), np.int32)
+    for b in range(B):
+        ids[b, :lens[b]] = rng.integers(1, vocab, size=lens[b])
+    got = eng.forward_ids(ids, lens)
+    ref, ref_pooled, ref_h = _oracle_forward(state, layers, vocab, ids, lens)
+    cos = cosine_rows(got, ref)
+    assert cos.min() >= COS_MIN, cos
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+    # hidden states of the real tokens (bf16 activations vs fp32 oracle)
+    hid = eng.read_hidden(B * S).reshape(B, S, 768)
+    for b in range(B):
+        c = cosine_rows(hid[b, :lens[b]], ref_h[b, :lens[b]])
+        assert c.min() >= 0.998, (b, c.min())
+    # un-normalised pooling (normalize_embeddings=False)
+    raw = eng.forward_ids(ids, lens, normalise=False)
+    assert cosine_rows(raw, ref_pooled).min() >= COS_MIN
+    np.testing.assert_allclose(np.linalg.norm(raw, axis=1), np.linalg.norm(ref_pooled, axis=1), rtol=2e-2)
+
+
+def test_padding_does_not_change_a_sentence(small):
+    eng, state, layers, vocab = small
+    rng = np.random.default_rng(5)
+    row = rng.integers(1, vocab, size=19).astype(np.int32)
+    a = eng.forward_ids(row[None, :], np.array([19], np.int32))
+    ids = np.zeros((4, 64), np.int32)
+    ids[:, :19] = row
+    ids[1:, 19:40] = rng.integers(1, vocab, size=(3, 21))
+    b = eng.forward_ids(ids, np.array([19, 40, 40, 40], np.int32))
+    assert cosine_rows(a, b[:1]).min() >= 0.99999
+
+
+def test_device_tensors_and_large_batch(small):
+    import torch
+    eng, state, layers, vocab = small
+    B, S = 128, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ids = torch.randint(1, vocab, (B, S), generator=g, device="cuda", dtype=torch.int32)
+    lens = torch.full((B,), S, dtype=torch.int32, device="cuda")
+    out = eng.forward_ids(ids, lens)
+    torch.cuda.synchronize()
+    assert out.is_cuda and out.shape == (B, 768)
+    ref, _, _ = _oracle_forward(state, layers, vocab, ids.cpu().numpy(), lens.cpu().numpy())
+    assert cosine_rows(out.cpu().numpy(), ref).min() >= COS_MIN
+
+
+@pytest.fixture(scope="module")
+def full12(tmp_path_factory):
+    """12-layer synthetic model + synthetic vocab over the real ICD texts, saved as an HF dir."""
+    N, E, W = _mods()
+    recs = otext.load_records(os.path.join(ROOT, "data", "ICD_10v601.csv"))
+    texts = [otext.query_text(r["semantic_text"]) for r in recs]
+    vocab = oenc.make_vocab(texts)
+    state = oenc.synthetic_state_dict(seed=0, num_layers=12, vocab_size=len(vocab))
+    d = str(tmp_path_factory.mktemp("model"))
+    oenc.save_hf_dir(d, state, vocab, 12)
+    eng = E.EncoderEngine(d, device="cuda")
+    oracle = oenc.OracleEncoder(state, os.path.join(d, "vocab.txt"), 12)
+    yield eng, oracle, texts
+    eng.close()
+
+
+def test_real_icd_texts_12_layers(full12):
+    eng, oracle, texts = full12
+    rng = np.random.default_rng(0)
+    longest = sorted(range(len(texts)), key=lambda j: -len(texts[j]))[:8]  # these truncate at 128 tokens
+    pick = list(rng.choice(len(texts), size=56, replace=False)) + longest
+    sample = [texts[j] for j in pick]
+    ref = oracle.encode(sample, batch_size=32)
+    got = eng.encode(sample, batch_size=32, show_progress_bar=False, normalize_embeddings=True)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    cos = cosine_rows(got, ref)
+    assert cos.min() >= COS_MIN, (cos.min(), np.argmin(cos))
+    one = eng.encode(sample[3], normalize_embeddings=True)
+    assert one.shape == (768,)
+    assert cosine_rows(one[None], ref[3:4]).min() >= COS_MIN
+    assert eng.get_sentence_embedding_dimension() == 768 and eng.max_seq_length == 128
+    assert eng.encode([], normalize_embeddings=True).shape == (0, 768)
+
+
+def test_search_over_encoded_corpus_matches_oracle_search(full12):
+    """End of the hot path: ids of the top-10 over GPU embeddings == exact fp32 search over the
+    ORACLE's embeddings, up to swaps among scores tied within 1e-3 (BASELINE north_star)."""
+    from oracle import search as osearch
+    from parity import check_topk
+    eng, oracle, texts = full12
+    rng = np.random.default_rng(1)
+    pick = rng.choice(len(texts), size=1500, replace=False)
+    corpus_t = [texts[j] for j in pick]
+    ref_c = oracle.encode(corpus_t, batch_size=64)
+    got_c = eng.encode(corpus_t, normalize_embeddings=True)
+    queries = [otext.query_text(t.split(" | ")[0][7:]) for t in corpus_t[:40]]
+    ref_q = oracle.encode(queries, batch_size=64)
+    got_q = eng.encode(queries, normalize_embeddings=True)
+    VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    N = importlib.import_module("rag-project-icd10_b200._native")
+    idx = VectorIndex(768, device=0, keep_f32=True)
+    idx.append(got_c, np.ones(len(got_c), np.uint8))
+    _, raw, ids = idx.search(got_q, 10, weight_mode=N.WEIGHT_NONE)
+    ref_s, ref_i = osearch.exact_topk(ref_c, ref_q, 10)
+    check_topk(ids, raw, ref_i, ref_s, lambda b, i: ref_c[np.asarray(i)] @ ref_q[b], tie_tol=3e-3, score_tol=3e-3)
+    idx.close()
