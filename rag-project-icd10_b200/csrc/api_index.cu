@@ -147,6 +147,9 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
       a.part_id = (int*)x->part_id.ptr;
       a.P = P;
       a.groups_used = &P_used;
+      ICD_TRY(x->gbound.reserve((size_t)B * 4));
+      ICD_CUDA(cudaMemsetAsync(x->gbound.ptr, 0x80, (size_t)B * 4, st));
+      a.gbound = (int*)x->gbound.ptr;
       ICD_TRY(launch_tensor_scan(a, x->tmap, st));
     } else {
       const int per = stream_scan_max_queries(scan_f32rows, x->dim);
@@ -307,6 +310,7 @@ int icd_index_destroy(icd_index* x) {
   x->cand_id.release();
   x->out_stage.release();
   x->in_stage.release();
+  x->gbound.release();
   for (int i = 0; i < 4; ++i) cudaEventDestroy(x->ev[i]);
   delete x;
   return ICD_OK;

@@ -31,7 +31,7 @@ struct icd_index {
   bool map_valid = false;
   int64_t map_rows = 0;
   // workspace
-  icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage;
+  icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage, gbound;
   // stage timing (scan, merge, finalise)
   cudaEvent_t ev[4];
   bool timing = false, timing_pending = false;

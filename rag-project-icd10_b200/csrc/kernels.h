@@ -39,6 +39,7 @@ struct TensorScanArgs {
   int* part_id;       // [B, P, k]
   int P;              // partial lists per query the buffers were sized for (>= groups used)
   int* groups_used;   // out: partial lists actually written per query
+  int* gbound;        // [B] ints, pre-set to 0x80808080 (a very negative key), or null to disable pruning
 };
 int tensor_scan_max_partials();
 bool tensor_scan_supported(int dim, int k);

@@ -7,14 +7,25 @@
 //   * a CTA owns one tile of 128 queries for its whole life.  The tile lives in TENSOR MEMORY
 //     as the MMA A operand (128 lanes x dim/2 columns of packed bf16, <= 384 columns), so
 //     shared memory is free for streaming the table.
-//   * table rows stream HBM -> shared memory through TMA (64 rows x 64 bf16 boxes, 128-byte
-//     swizzle) in a ring of mbarrier-tracked stages and are the MMA B operand (K-major).
-//   * tcgen05.mma (M=128 queries, N=64 rows, K=16) accumulates a 128x64 fp32 tile in TMEM;
-//     two accumulator buffers let the MMA of tile t+1 overlap the epilogue of tile t.
+//   * table rows stream HBM -> shared memory through TMA in a ring of mbarrier-tracked stages
+//     and are the MMA B operand (K-major).  The table is described to TMA as a 3-D tensor
+//     {64 elements, rows, K blocks} so ONE bulk copy brings a whole stage -- 64 rows x (kbs x 64)
+//     bf16, laid out as kbs consecutive 128 x 64 tiles in the 128-byte-swizzle canonical layout.
+//   * tcgen05.mma (M=128 queries, N=128 rows, K=16) accumulates a 128x128 fp32 tile in TMEM.
+//     N must be >= 128: with A in TMEM every MMA re-reads the 128x16 A slice (4 KiB) at the
+//     TMEM read rate, ~64 cycles, so N=64 (32 cycles of math) runs the pipe at half rate
+//     (measured: 38 % tensor-active with N=64).  The accumulators take the columns Q leaves
+//     free: one buffer for dim=768 (the epilogue drains it to registers at once and hands it
+//     back), two for dim <= 512.
 //   * epilogue: thread == TMEM lane == query.  It reads its 64 scores with tcgen05.ld,
 //     compares against its private k-th best (a register) and only on the rare hit inserts
 //     into its private sorted list in shared memory.  Level weights (ICD_WEIGHT_PRE) are
 //     applied here.
+//   * cross-CTA pruning: every CTA publishes its k-th best score per query to a global bound
+//     (atomicMax on an order-preserving integer key) and admits a row only if it also reaches
+//     the bound the other row groups have proven; without it each of the 148 row groups warms
+//     its own lists and the insert path, not HBM, bounds the kernel (ncu, B=128: 42 % of
+//     epilogue samples in the insert loop, 57 % DRAM utilisation).
 //   * grid = G row groups x T query tiles; each CTA writes one sorted list per query to the
 //     partial buffer [B, G, k] that topk_merge.cu reduces.
 //
@@ -34,13 +45,12 @@ namespace icd {
 namespace {
 
 constexpr int BM = 128;  // queries per CTA
-constexpr int BN = 64;   // table rows per accumulator tile
+constexpr int BN = 128;  // table rows per accumulator tile
 constexpr int BK = 64;   // bf16 per TMA box row (128 bytes)
-constexpr int kStageBytes = BN * BK * 2;  // 8 KiB
-constexpr int kMaxStages = 24;
+constexpr int kBoxBytes = BN * BK * 2;  // one 128 x 64 bf16 tile: 16 KiB
+constexpr int kMaxStages = 12;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
-constexpr int kAccCol0 = 384;  // accumulators live behind the query tile
 constexpr int kSmemLimit = 227 * 1024;
 
 struct ScanParams {
@@ -48,17 +58,24 @@ struct ScanParams {
   const __nv_bfloat16* q;  // [B, dim]
   float* part_score;       // [B, G, kc]
   int* part_id;
+  int* gbound;             // [B] order-preserving keys of the proven per-query k-th-best bound, or null
   int64_t n_rows;
   int dim, nkb;  // nkb = dim / 64
   int B, kc, weight_pre;
   int G, T;      // row groups, query tiles in this launch
   int qt0;       // first query tile of this launch
   int nst;       // pipeline stages
+  int kbs;       // K blocks (128 x 64 tiles) per stage; divides nkb
+  int nacc;      // accumulator buffers (1 or 2) in the TMEM columns behind the query tile
+  int acc_col0;  // first accumulator column (== dim / 2 rounded up to 128)
 };
 
+// Private candidate list of one query (thread): kc entries sorted by (score desc, id asc) in
+// shared memory, entry j of this thread at [j * BM].  Rows arrive in ascending id order, so a
+// strict '>' admission test plus "insert after equal scores" keeps the id tie-break exact.
+// (An unsorted list with worst-slot tracking was measured slower: 60 % vs 71 % of HBM at B=128.)
 __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, int id) {
-  // private sorted list, entry j of this thread at [j * BM]; precondition s > ls[(kc-1)*BM]
-  int j = kc - 1;
+  int j = kc - 1;  // precondition: s > ls[(kc-1)*BM]
   while (j > 0 && ls[(j - 1) * BM] < s) {
     ls[j * BM] = ls[(j - 1) * BM];
     li[j * BM] = li[(j - 1) * BM];
@@ -69,6 +86,13 @@ __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, i
   return ls[(kc - 1) * BM];
 }
 
+// order-preserving float <-> int key (signed int compare == float compare, -0 < +0 harmless)
+__device__ __forceinline__ int float_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -77,8 +101,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   const int qt = p.qt0 + blockIdx.x % p.T;
 
   // shared memory carve-up
-  unsigned char* stage_base = smem;                                           // nst * 8 KiB, 1024-aligned
-  float* list_s = reinterpret_cast<float*>(smem + (size_t)p.nst * kStageBytes);  // [kc][BM]
+  const int stage_bytes = p.kbs * kBoxBytes;
+  unsigned char* stage_base = smem;                                           // nst stages, 1024-aligned
+  float* list_s = reinterpret_cast<float*>(smem + (size_t)p.nst * stage_bytes);  // [kc][BM]
   int* list_i = reinterpret_cast<int*>(list_s + (size_t)p.kc * BM);           // [kc][BM]
   uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + (size_t)p.kc * BM);
   uint64_t* full_bar = bars;                    // [nst]
@@ -158,11 +183,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       uint32_t phase = 0;
       for (int64_t t = t0; t < t1; ++t) {
         const int row = (int)(t * BN);
-        for (int kb = 0; kb < p.nkb; ++kb) {
+        for (int kb = 0; kb < p.nkb; kb += p.kbs) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-          ptx::mbar_expect_tx(fb, kStageBytes);
-          ptx::tma_load_2d(ptx::smem_u32(stage_base + (size_t)stage * kStageBytes), &tmap, fb, kb * BK, row);
+          ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
+          ptx::tma_load_3d(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
           if (++stage == p.nst) {
             stage = 0;
             phase ^= 1;
@@ -178,19 +203,24 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       uint32_t phase = 0;
       int it = 0;
       for (int64_t t = t0; t < t1; ++t, ++it) {
-        const int buf = it & 1;
-        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1);
+        const int buf = (p.nacc == 2) ? (it & 1) : 0;
+        const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;  // n-th use of this buffer
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[buf]), (use & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(kAccCol0 + buf * BN);
-        for (int kb = 0; kb < p.nkb; ++kb) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc_col0 + buf * BN);
+        for (int kb = 0; kb < p.nkb; kb += p.kbs) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(stage_base + (size_t)stage * kStageBytes);
+          const uint32_t sa = ptx::smem_u32(stage_base + (size_t)stage * stage_bytes);
+          const uint64_t desc0 = ptx::make_desc_k128(sa);
+          for (int j = 0; j < p.kbs; ++j) {
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            const uint64_t bdesc = ptx::make_desc_k128(sa + k4 * 32);
-            const uint32_t a_tmem = tmem_base + (uint32_t)((kb * (BK / 16) + k4) * 8);
-            ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | k4) ? 1u : 0u);
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              // +2 per 32 bytes of K inside the 128-byte swizzle row, +512 per 8 KiB tile (16-byte units)
+              const uint64_t bdesc = desc0 + (uint64_t)(j * (kBoxBytes >> 4) + k4 * 2);
+              const uint32_t a_tmem = tmem_base + (uint32_t)(((kb + j) * (BK / 16) + k4) * 8);
+              ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+            }
           }
           ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // frees the stage when the MMAs retire
           if (++stage == p.nst) {
@@ -204,41 +234,69 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   } else {
     // ===================== epilogue: fused top-k =====================
     const bool live = query < p.B;
-    float thr = live ? -INFINITY : INFINITY;
+    float thr = live ? -INFINITY : INFINITY;  // k-th best of this CTA's list (strict admission)
+    float adm = thr;                          // admission threshold: max(thr, just below the global bound)
+    float published = -INFINITY;
+    int* gb = (p.gbound && live) ? p.gbound + query : nullptr;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     int it = 0;
     for (int64_t t = t0; t < t1; ++t, ++it) {
-      const int buf = it & 1;
-      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
+      if (gb) {
+        // bound proven by any row group: rows strictly below it cannot reach the global top-k
+        // (equal scores are still admitted: the id tie-break is decided at the merge)
+        int key;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(key) : "l"(gb));
+        const float bound = key_float(key);
+        adm = fmaxf(thr, nextafterf(bound, -INFINITY));
+      }
+      const int buf = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), use & 1);
       ptx::tc_fence_after();
+      // drain the whole 128-column accumulator row to registers, then hand the buffer back
       uint32_t r[BN];
-      const uint32_t acc = lane_addr + (uint32_t)(kAccCol0 + buf * BN);
-      ptx::tmem_ld_32x32b_x32(acc, r);
-      ptx::tmem_ld_32x32b_x32(acc + 32, r + 32);
+      const uint32_t acc = lane_addr + (uint32_t)(p.acc_col0 + buf * BN);
+#pragma unroll
+      for (int c32 = 0; c32 < BN / 32; ++c32) ptx::tmem_ld_32x32b_x32(acc + c32 * 32, r + c32 * 32);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));  // accumulator may be overwritten
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
 
       const int64_t row0 = t * BN;
       const int valid = (int)min((int64_t)BN, p.n_rows - row0);
-      if (p.weight_pre) {
-        // level bytes of the 64 rows of this tile (same for every thread: broadcast loads)
 #pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          const uint8_t lv = (c < valid) ? p.levels[row0 + c] : (uint8_t)2;
-          r[c] = __float_as_uint(__uint_as_float(r[c]) * level_weight_f(lv));
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        if (p.weight_pre) {
+          // level bytes of these 32 rows (same for every thread: broadcast loads)
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int cc = c32 * 32 + c;
+            const uint8_t lv = (cc < valid) ? p.levels[row0 + cc] : (uint8_t)2;
+            r[cc] = __float_as_uint(__uint_as_float(r[cc]) * level_weight_f(lv));
+          }
+        }
+        float m8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m8[c] = __uint_as_float(r[c32 * 32 + c]);
+#pragma unroll
+        for (int c = 8; c < 32; ++c) m8[c & 7] = fmaxf(m8[c & 7], __uint_as_float(r[c32 * 32 + c]));
+        const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        if (m > adm) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int cc = c32 * 32 + c;
+            const float s = __uint_as_float(r[cc]);
+            if (s > adm && cc < valid) {
+              thr = list_insert(my_s, my_i, p.kc, s, (int)(row0 + cc));
+              adm = fmaxf(adm, thr);
+            }
+          }
         }
       }
-      float m = __uint_as_float(r[0]);
-#pragma unroll
-      for (int c = 1; c < BN; ++c) m = fmaxf(m, __uint_as_float(r[c]));
-      if (m > thr) {
-#pragma unroll
-        for (int c = 0; c < BN; ++c) {
-          const float s = __uint_as_float(r[c]);
-          if (s > thr && c < valid) thr = list_insert(my_s, my_i, p.kc, s, (int)(row0 + c));
-        }
+      if (gb && thr > published) {
+        atomicMax(gb, float_key(thr));
+        published = thr;
       }
     }
     // one sorted list per (query, group)
@@ -260,8 +318,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   }
 }
 
-size_t smem_bytes(int nst, int kc) {
-  return (size_t)nst * kStageBytes + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
+size_t smem_bytes(int nst, int kbs, int kc) {
+  return (size_t)nst * kbs * kBoxBytes + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
 }
 
 }  // namespace
@@ -298,14 +356,50 @@ int make_tmap_bf16_2d(void* map128, const void* base, uint64_t rows, uint64_t co
   return ICD_OK;
 }
 
+int make_tmap_bf16_3d(void* map128, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ICD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+  if (!sym || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ICD_E_CUDA;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeFn>(sym)(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                               3, const_cast<void*>(base), gdim, gstride, box, estride,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+    return ICD_E_CUDA;
+  }
+  return ICD_OK;
+}
+
 int tensor_scan_max_partials() { return kSMs; }
 
 bool tensor_scan_supported(int dim, int k) {
   return dim % BK == 0 && dim >= BK && dim <= 768 && k >= 1 && k <= ICD_MAX_K;
 }
 
+static int stage_kblocks(int dim) {
+  const int nkb = dim / BK;
+  for (int kbs = 2; kbs > 1; --kbs)
+    if (nkb % kbs == 0) return kbs;
+  return 1;
+}
+
 int tensor_scan_make_map(void* map128, const void* table, int64_t n_rows, int dim) {
-  return make_tmap_bf16_2d(map128, table, (uint64_t)n_rows, (uint64_t)dim, BN, BK, true);
+  // 3-D view {64 elements, rows, K blocks}: strides {dim*2 bytes, 128 bytes}
+  return make_tmap_bf16_3d(map128, table, BK, (uint64_t)n_rows, (uint64_t)(dim / BK), (uint64_t)dim * 2, BK * 2, BK, BN,
+                           (uint32_t)stage_kblocks(dim));
 }
 
 int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
@@ -322,13 +416,14 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
   *a.groups_used = G;
 
   // pipeline depth from the shared memory left after the per-thread lists
+  const int kbs = stage_kblocks(a.dim);
   int nst = kMaxStages;
-  while (nst > 2 && smem_bytes(nst, a.k) > (size_t)kSmemLimit) --nst;
-  if (smem_bytes(nst, a.k) > (size_t)kSmemLimit) {
+  while (nst > 2 && smem_bytes(nst, kbs, a.k) > (size_t)kSmemLimit) --nst;
+  if (smem_bytes(nst, kbs, a.k) > (size_t)kSmemLimit) {
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
-  const size_t smem = smem_bytes(nst, a.k);
+  const size_t smem = smem_bytes(nst, kbs, a.k);
   ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CUtensorMap tmap;
   memcpy(&tmap, map128, sizeof(CUtensorMap));
@@ -338,6 +433,7 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
     p.q = reinterpret_cast<const __nv_bfloat16*>(a.q_bf16);
     p.part_score = a.part_score;
     p.part_id = a.part_id;
+    p.gbound = a.gbound;
     p.n_rows = a.n_rows;
     p.dim = a.dim;
     p.nkb = a.dim / BK;
@@ -348,6 +444,9 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
     p.T = std::min(T_launch, T_total - qt0);
     p.qt0 = qt0;
     p.nst = nst;
+    p.kbs = kbs;
+    p.acc_col0 = ((a.dim / 2 + 127) / 128) * 128;
+    p.nacc = (kTmemCols - p.acc_col0) / BN >= 2 ? 2 : 1;
     scan_tc_kernel<<<G * p.T, kThreads, smem, st>>>(tmap, p);
     count_launch();
     ICD_CUDA(cudaGetLastError());

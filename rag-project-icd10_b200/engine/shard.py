@@ -24,18 +24,16 @@ class ShardGroup:
         if world > 1:
             if rank == 0:
                 N.check(N.lib().icd_nccl_unique_id(N.buf_ptr(idbuf)), "icd_nccl_unique_id")
-            obj = [idbuf.tobytes()]
-            dist.broadcast_object_list(obj, src=0)
-            idbuf = np.frombuffer(obj[0], np.uint8).copy()
+            ident, _ = bootstrap_exchange(dist, rank, world, idbuf.tobytes() if rank == 0 else None, None, share_ident=True)
+            idbuf = np.frombuffer(ident, np.uint8).copy()
         N.check(N.lib().icd_shard_group_create(N.buf_ptr(idbuf) if world > 1 else None, rank, world, int(row_offset),
                                                index._h, C.byref(self._h)), "icd_shard_group_create")
         self.peer_ready = False
         if world > 1 and peer_slabs:
             mine = np.zeros(64, np.uint8)
             N.check(N.lib().icd_shard_group_export_slab(self._h, N.buf_ptr(mine)), "icd_shard_group_export_slab")
-            allh = [None] * world
-            dist.all_gather_object(allh, mine.tobytes())
-            table = np.frombuffer(b"".join(allh), np.uint8).copy()
+            _, table_b = bootstrap_exchange(dist, rank, world, None, mine.tobytes())
+            table = np.frombuffer(table_b, np.uint8).copy()
             N.check(N.lib().icd_shard_group_import_slabs(self._h, N.buf_ptr(table)), "icd_shard_group_import_slabs")
             self.peer_ready = True
             dist.barrier()
@@ -75,6 +73,22 @@ class ShardGroup:
 
 
 N_ID_BYTES = 128
+
+
+def bootstrap_exchange(dist, rank: int, world: int, ident, handle, share_ident: bool = False):
+    """Start-up plumbing over torch.distributed (any backend): rank 0's NCCL id to everyone
+    (share_ident=True; ident is only read on rank 0) and/or an all-gather of one opaque 64-byte handle per rank.
+    Returns (ident_bytes | None, concatenated_handles | None)."""
+    out_ident, out_table = None, None
+    if share_ident:
+        obj = [ident if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        out_ident = obj[0]
+    if handle is not None:
+        allh = [None] * world
+        dist.all_gather_object(allh, handle)
+        out_table = b"".join(allh)
+    return out_ident, out_table
 
 
 def shard_bounds(total_rows: int, rank: int, world: int):
