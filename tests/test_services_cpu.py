@@ -1,0 +1,124 @@
+"""Host logic of the drop-in services, on CPU (no GPU, no library compute calls): text
+preparation, CSV rules of the build tool, C-ABI export list, loud failure without a GPU."""
+import ctypes
+import hashlib
+import importlib
+import json
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden(name):
+    with open(os.path.join(ROOT, "tests", "golden", name), encoding="utf-8") as fh:
+        return json.load(fh)
+
+
+def test_library_exports_every_declared_symbol(native):
+    """include/icdrag.h <-> libicdrag.so: every declared function is exported (no compute calls)."""
+    hdr = open(os.path.join(ROOT, "include", "icdrag.h")).read()
+    declared = sorted(set(re.findall(r"\b(icd_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(native.SYMBOLS)
+    assert os.path.exists(native.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert native.lib().icd_version() >= 100
+
+
+def test_no_gpu_fails_loudly(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    idx = importlib.import_module("rag-project-icd10_b200.engine.index")
+    with pytest.raises(native.NativeError):
+        idx.VectorIndex(768)
+    enc = importlib.import_module("rag-project-icd10_b200.engine.encoder")
+    with pytest.raises(native.NativeError):
+        enc.EncoderEngine("does-not-matter")
+    store = importlib.import_module("rag-project-icd10_b200.engine.store")
+    with pytest.raises(native.NativeError):
+        store.IcdStoreClient(uri="/tmp/x.db")
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "rag-project-icd10_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+            hits = [l for l in src.splitlines() if re.match(r"\s*(from|import)\s+oracle\b", l)]
+            if fn == "encoder.py":
+                # engine/encoder.py::smoke() is the one sanctioned checker call site (__graft_entry__.smoke)
+                head = src.split("def smoke()")[0]
+                assert not [l for l in head.splitlines() if re.match(r"\s*(from|import)\s+oracle\b", l)]
+                assert len(hits) <= 1, hits
+            else:
+                assert not hits, (fn, hits)
+
+
+def test_build_tool_records_match_reference():
+    B = importlib.import_module("rag-project-icd10_b200.tools.build_database")
+    g = _golden("records_golden.json")
+    b = B.DatabaseBuilder.__new__(B.DatabaseBuilder)
+    recs = b.load_csv_data(os.path.join(ROOT, "data", "ICD_10v601.csv"))
+    assert len(recs) == g["count"]
+    canon = json.dumps(recs, ensure_ascii=False, sort_keys=True).encode("utf-8")
+    assert hashlib.sha256(canon).hexdigest() == g["sha256"]
+    for n, want in g["batch_sizes"].items():
+        assert b._calculate_optimal_batch_size(int(n)) == want
+
+
+def test_embedding_service_text_rules_and_errors():
+    E = importlib.import_module("rag-project-icd10_b200.services.embedding_service")
+    g = _golden("embedding_service_golden.json")
+
+    class Rec:
+        max_seq_length = 128
+        calls = []
+
+        def __init__(self, name, device=None):
+            self.name, self.device = name, device
+
+        def get_sentence_embedding_dimension(self):
+            return 8
+
+        def encode(self, texts, **kw):
+            import numpy as np
+            Rec.calls.append({"texts": texts, "kwargs": {k: kw[k] for k in sorted(kw)}})
+            n = 1 if isinstance(texts, str) else len(texts)
+            out = np.ones((n, 8), np.float32)
+            return out[0] if isinstance(texts, str) else out
+
+    old = E.EmbeddingService.engine_factory
+    E.EmbeddingService.engine_factory = Rec
+    os.environ["EMBEDDING_MODEL_NAME"] = "shibing624/text2vec-base-chinese"
+    os.environ["EMBEDDING_DEVICE"] = "cpu"
+    try:
+        es = E.EmbeddingService()
+        probe = ["急性胃肠炎", "query: 已带前缀", "passage: 已带前缀", "", " 前导空格", "Query: 大写不算"]
+        for t in probe:
+            es.encode_single(t)
+            es.encode_query(t)
+        assert es.encode_batch([]) == g["outs"]["encode_batch_empty"]
+        eb = es.encode_batch(probe, show_progress=False)
+        assert [type(eb).__name__, type(eb[0]).__name__, type(eb[0][0]).__name__] == g["outs"]["encode_batch_type"]
+        es.encode_icd_record({"code": "A00", "preferred_zh": "霍乱"})
+        es.encode_icd_record({"code": "A00", "preferred_zh": "  "})
+        es.encode_icd_record({"preferred_zh": ""})
+        assert es.get_model_info() == g["model_info"]
+        te = es.test_embedding("测试")
+        assert sorted(te.keys()) == g["test_embedding_keys"] and list(te["embedding_shape"]) == g["test_embedding_shape"]
+        assert Rec.calls == g["calls"]           # every text and kwarg the reference sends its engine
+        es.model = None
+        with pytest.raises(RuntimeError, match="嵌入模型未加载"):
+            es.encode_single("x")
+        with pytest.raises(RuntimeError):
+            es.encode_batch(["x"])
+        assert es.get_model_info() == {"loaded": False}
+    finally:
+        E.EmbeddingService.engine_factory = old

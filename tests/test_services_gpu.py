@@ -1,0 +1,167 @@
+"""GPU tests of the drop-in services through the reference-facing API: MilvusService against
+the reference-generated golden (tests/golden/milvus_service_golden.json), persistence, and the
+build tool end to end (CSV subset -> GPU encoder -> store -> search) against the oracle."""
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import encoder as oenc
+from oracle import search as osearch
+from oracle import text as otext
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden(name):
+    with open(os.path.join(ROOT, "tests", "golden", name), encoding="utf-8") as fh:
+        return json.load(fh)
+
+
+class _Emb8:
+    def encode_query(self, q):
+        return np.ones(8, np.float32) / np.sqrt(8.0)
+
+
+def _close(a, b, tol=1e-6):
+    if isinstance(a, dict):
+        assert set(a) == set(b), (a.keys(), b.keys())
+        for k in a:
+            _close(a[k], b[k], tol)
+    elif isinstance(a, float) or isinstance(b, float):
+        assert abs(float(a) - float(b)) <= tol, (a, b)
+    else:
+        assert a == b, (a, b)
+
+
+def test_milvus_service_reproduces_reference_golden(tmp_path, monkeypatch):
+    g = _golden("milvus_service_golden.json")
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "db" / "milvus.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "icd10_golden")
+    monkeypatch.setenv("MILVUS_MODE", "local")
+    M = importlib.import_module("rag-project-icd10_b200.services.milvus_service")
+    ms = M.MilvusService(embedding_service=_Emb8())
+    assert ms.dimension == g["dimension"] == 8
+    recs = {r["code"]: r for r in otext.load_records(os.path.join(ROOT, "data", "ICD_10v601.csv"))}
+    sub = [recs[c] for c in g["codes"]]
+    vecs = np.asarray(g["vectors"], np.float32)
+    assert ms.insert_records(sub, [v for v in vecs]) is g["insert_ok"] is True
+    for s in g["searches"]:
+        hits = ms.search(np.asarray(s["query"], np.float32), top_k=s["top_k"])
+        assert [h["code"] for h in hits] == [h["code"] for h in s["hits"]]
+        for a, b in zip(hits, s["hits"]):
+            _close(a, b)
+    # batched extension returns exactly the per-query results
+    qs = np.asarray([s["query"] for s in g["searches"] if s["top_k"] == 5], np.float32)
+    batch = ms.search_batch(qs, top_k=5)
+    for row, s in zip(batch, [s for s in g["searches"] if s["top_k"] == 5]):
+        assert [h["code"] for h in row] == [h["code"] for h in s["hits"]]
+    with pytest.raises(ValueError, match="记录数量与向量数量不匹配"):
+        ms.insert_records(sub[:2], [vecs[0]])
+    assert ms.insert_records(sub[:1], [[0.0] * 8]) is False      # plain list: no .tolist(), as in the reference
+    assert ms.get_collection_stats() == g["stats"]
+    mem = ms.get_memory_usage()
+    assert mem["num_entities"] == 207 and abs(mem["estimated_memory_mb"] - g["memory_usage"]["estimated_memory_mb"]) < 1e-12
+    assert set(mem) == set(g["memory_usage"])
+    assert ms.get_collection_load_state()["loaded"] is True     # see DESIGN.md: the reference compares to "Loaded"
+    tc = ms.test_connection()
+    assert tc["connected"] and tc["collection_stats"] == g["stats"] and tc["client_type"] == "MilvusClient"
+    assert sorted(ms.health_check().keys()) == g["health_keys"] and ms.health_check()["healthy"] is True
+    assert {k: ms._calculate_level_weight(int(k)) for k in g["level_weights"]} == g["level_weights"]
+    _close(ms.release_collection(), g["release"])
+    assert ms.get_collection_load_state()["loaded"] is False
+    assert ms.search(np.asarray(g["searches"][0]["query"], np.float32), 5) == []   # not loaded -> degrade to []
+    assert ms.load_collection() is True
+    assert len(ms.search(np.asarray(g["searches"][0]["query"], np.float32), 5)) == 5
+    ms.disconnect()
+    # persistence: a new service over the same path sees the rows (append semantics: re-insert duplicates)
+    ms2 = M.MilvusService(embedding_service=_Emb8())
+    assert ms2.get_collection_stats()["num_entities"] == 207
+    s0 = g["searches"][2]
+    assert [h["code"] for h in ms2.search(np.asarray(s0["query"], np.float32), s0["top_k"])] == [h["code"] for h in s0["hits"]]
+    assert ms2.insert_records(sub[:3], [v for v in vecs[:3]]) is True
+    assert ms2.get_collection_stats()["num_entities"] == 210
+    assert ms2.clear_collection() is True and ms2.get_collection_stats()["num_entities"] == 0
+    assert ms2.search(np.asarray(s0["query"], np.float32), 5) == []
+    ms2.disconnect()
+
+
+def test_search_never_raises(tmp_path, monkeypatch):
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "m.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "c")
+    M = importlib.import_module("rag-project-icd10_b200.services.milvus_service")
+    ms = M.MilvusService(embedding_service=_Emb8())
+    assert ms.search(np.zeros(5, np.float32), 3) == []          # wrong dimension -> logged, []
+    assert ms.search(np.zeros(8, np.float32), 3) == []          # empty collection
+    ms.disconnect()
+
+
+@pytest.fixture(scope="module")
+def model_dir(tmp_path_factory):
+    recs = otext.load_records(os.path.join(ROOT, "data", "ICD_10v601.csv"))
+    texts = [otext.query_text(r["semantic_text"]) for r in recs]
+    vocab = oenc.make_vocab(texts)
+    state = oenc.synthetic_state_dict(seed=1, num_layers=4, vocab_size=len(vocab))
+    d = str(tmp_path_factory.mktemp("model4"))
+    oenc.save_hf_dir(d, state, vocab, 4)
+    return d, state
+
+
+def test_build_database_end_to_end(tmp_path, monkeypatch, model_dir):
+    d, state = model_dir
+    # CSV subset in the reference's format (utf-8 with BOM, columns code,disease)
+    src = open(os.path.join(ROOT, "data", "ICD_10v601.csv"), encoding="utf-8-sig").read().splitlines()
+    sub_csv = tmp_path / "subset.csv"
+    sub_csv.write_text("﻿" + "\n".join(src[:1301]) + "\n", encoding="utf-8")
+    monkeypatch.setenv("EMBEDDING_MODEL_NAME", d)
+    monkeypatch.setenv("EMBEDDING_DEVICE", "auto")
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "db" / "icd.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "icd10")
+    monkeypatch.chdir(tmp_path)
+    B = importlib.import_module("rag-project-icd10_b200.tools.build_database")
+    assert B.main(["--input", str(sub_csv), "--rebuild"]) is True
+    builder = B.DatabaseBuilder()
+    builder.initialize_services()
+    ver = builder.verify_database()
+    assert ver["database_stats"]["num_entities"] == 1300 and ver["search_test"]["results_count"] == 5
+    es, ms = builder.embedding_service, builder.milvus_service
+    assert es.get_model_info()["embedding_dimension"] == 768 and es.device == "cuda"
+
+    # oracle: same texts through the CPU encoder, exact fp32 search, reference re-rank
+    recs = otext.load_records(str(sub_csv))
+    oracle = oenc.OracleEncoder(state, os.path.join(d, "vocab.txt"), 4)
+    ref_c = oracle.encode([otext.query_text(r["semantic_text"]) for r in recs], batch_size=64)
+    from parity import COS_MIN, cosine_rows
+    stored = ms.client.cols["icd10"].index.read(0, 1300)
+    assert cosine_rows(stored, ref_c).min() >= COS_MIN
+    for probe in ("急性胃肠炎", "霍乱", "伤寒", "结核性脑膜炎", recs[700]["preferred_zh"]):
+        qv = es.encode_query(probe)
+        ref_q = oracle.encode(otext.query_text(probe))
+        assert float(qv @ ref_q) >= COS_MIN
+        hits = ms.search(qv, top_k=10)
+        want = osearch.search_hits(ref_c, recs, ref_q, 10)
+        # ids identical up to swaps among scores tied within 1e-3 (north_star rule), judged on oracle scores
+        want_raw = {h["code"]: h["original_score"] for h in want}
+        full = ref_c @ ref_q
+        kth = sorted(full, reverse=True)[9]
+        code_row = {r["code"]: i for i, r in enumerate(recs)}
+        for h in hits:
+            assert full[code_row[h["code"]]] >= kth - 3e-3, (probe, h["code"])
+            assert abs(h["original_score"] - full[code_row[h["code"]]]) <= 3e-3
+            assert h["title"] == recs[code_row[h["code"]]]["preferred_zh"]
+            assert abs(h["score"] - h["original_score"] * otext.level_weight(h["metadata"]["level"])) < 1e-6
+        assert [h["score"] for h in hits] == sorted((h["score"] for h in hits), reverse=True)
+        assert len(set(want_raw) & {h["code"] for h in hits}) >= 8
+    # --verify-only on the persisted store, fresh process state
+    ms.disconnect()
+    assert B.main(["--verify-only"]) is True
+    # incremental mode appends duplicates (reference :308-310, auto-id primary key)
+    assert B.main(["--input", str(sub_csv)]) is True
+    b2 = B.DatabaseBuilder()
+    b2.initialize_services()
+    assert b2.milvus_service.get_collection_stats()["num_entities"] == 2600
+    b2.milvus_service.disconnect()
