@@ -117,9 +117,24 @@ def make_queries(torch, batch, device, seed=999):
     return torch.nn.functional.normalize(q, dim=1).to(torch.bfloat16)
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core, so undo
+    that before numpy / BLAS load (and through threadpoolctl if they already have)."""
+    cores = os.cpu_count() or 1
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    return cores
+
+
 def cpu_sample(rows, batch, reps=1):
     """The reference's CPU search path (Milvus FLAT/IP restated: oracle.search.exact_topk, fp32
     numpy over all host threads) on a bounded sample of the workload."""
+    _use_all_host_threads()
     import numpy as np
     from oracle import search as osearch
     rng = np.random.default_rng(1234)
@@ -128,10 +143,10 @@ def cpu_sample(rows, batch, reps=1):
     corpus = osearch.bf16_round(corpus)
     q = rng.standard_normal((batch, DIM), dtype=np.float32)
     q /= np.linalg.norm(q, axis=1, keepdims=True)
-    osearch.exact_topk(corpus[: rows // 8], q[:8], K_TOP)  # warm BLAS threads
+    osearch.fast_topk(corpus[: rows // 8], q[:8], K_TOP)  # warm BLAS threads
     t0 = time.perf_counter()
     for _ in range(reps):
-        osearch.exact_topk(corpus, q, K_TOP)
+        osearch.fast_topk(corpus, q, K_TOP)
     dt = (time.perf_counter() - t0) / reps
     return dt
 
@@ -141,10 +156,11 @@ def run_reference(args, rank, world):
     fp32 exact IP + top-k; pymilvus/milvus-lite are not installable offline), host cores only."""
     if rank != 0:
         return
+    cores = _use_all_host_threads()
     import torch
+    torch.set_num_threads(cores)
     total_rows = args.rows
     sample_rows, sample_batch = args.cpu_rows, args.cpu_batch
-    cores = os.cpu_count() or 1
     times = []
     for i in range(args.warmup + args.steps):
         dt = cpu_sample(sample_rows, sample_batch)
@@ -163,11 +179,33 @@ def run_reference(args, rank, world):
                    "rows": total_rows, "dim": DIM, "batch": args.batch, "k": K_TOP},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "torch_threads": torch.get_num_threads(),
-                         "sample": f"{sample_batch} queries x {sample_rows} rows per step (numpy fp32 GEMM + exact "
-                                   f"top-k, oracle/search.py), extrapolated linearly in rows to {total_rows}"},
+                         "sample": f"{sample_batch} queries x {sample_rows} rows per step (numpy fp32 GEMM + argpartition "
+                                   f"top-k, oracle/search.py::fast_topk), extrapolated linearly in rows to {total_rows}"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on
+    stdout, so fd 1 is pointed at stderr for the run and the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -180,8 +218,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 stream, 2 tensor")
     ap.add_argument("--exchange", type=int, default=1, help="multi-GPU candidate exchange: 0 NCCL all-gather, 1 peer stores")
-    ap.add_argument("--cpu-rows", type=int, default=1_000_000)
-    ap.add_argument("--cpu-batch", type=int, default=128)
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000)
+    ap.add_argument("--cpu-batch", type=int, default=256)
+    ap.add_argument("--tune", default="", help="comma list of icd_tune knobs, e.g. scan_sample=0,scan_drift=0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
     args = ap.parse_args()
@@ -189,6 +228,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -198,6 +238,9 @@ def main():
     native = importlib.import_module("rag-project-icd10_b200._native")
     VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").VectorIndex
     native.require_gpu()
+    for kv in filter(None, args.tune.split(",")):
+        key, _, val = kv.partition("=")
+        native.tune(**{key.strip(): int(val)})
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -342,15 +385,15 @@ def main():
             line["cpu_baseline"] = {
                 "value": args.cpu_batch / dt * (args.cpu_rows / rows_total), "unit": "queries/s",
                 "cores": os.cpu_count(), "kind": "port",
-                "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows (numpy fp32 exact IP + top-k, "
-                          f"oracle/search.py), extrapolated linearly in rows to {rows_total}"}
+                "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows (numpy fp32 GEMM + argpartition top-k, "
+                          f"oracle/search.py::fast_topk), extrapolated linearly in rows to {rows_total}"}
         if not args.no_encoder:
             try:
                 enc_bench = importlib.import_module("rag-project-icd10_b200.engine.encoder").bench_encoder
                 line["encoder"] = enc_bench(dev, peaks)
             except Exception as e:  # encoder line is auxiliary; the headline must still print
                 line["encoder"] = {"error": repr(e)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -72,6 +72,11 @@ const char* icd_last_error(void);
 /* number of kernels this library has launched on the calling process so far (bench.py's gpu_launches) */
 int64_t icd_launch_count(void);
 int icd_device_count(void);
+/* process-wide tuning knobs of the tensor-core scan (tests and profiling; defaults are right for
+ * production): "scan_sample" (stride of the sampling pre-pass, 0 = off, -1 = by table size),
+ * "scan_drift" (tiles a CTA may run ahead of its row group, 0 = off), "scan_tmax" (query tiles per
+ * row stream per launch), "scan_bn" (64 | 128 rows per MMA tile), "scan_kbs" (K blocks per stage). */
+int icd_tune(const char* key, int value);
 
 /* ---------------------------------------------------------------- vector table + scan ------
  * Replaces the Milvus FLAT/IP collection: MilvusClient.insert (services/milvus_service.py:259)

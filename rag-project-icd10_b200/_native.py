@@ -25,7 +25,7 @@ MAX_K = 128
 
 # every symbol include/icdrag.h declares (tests check the library exports each one)
 SYMBOLS = [
-    "icd_version", "icd_last_error", "icd_launch_count", "icd_device_count",
+    "icd_version", "icd_last_error", "icd_launch_count", "icd_device_count", "icd_tune",
     "icd_index_create", "icd_index_destroy", "icd_index_append", "icd_index_adopt", "icd_index_clear",
     "icd_index_size", "icd_index_dim", "icd_index_read", "icd_index_search", "icd_index_last_timing",
     "icd_index_set_timing",
@@ -96,6 +96,7 @@ def _declare(L: C.CDLL) -> None:
     L.icd_last_error.restype = C.c_char_p
     L.icd_launch_count.restype = i64
     L.icd_device_count.restype = i32
+    L.icd_tune.argtypes = [C.c_char_p, i32]
     L.icd_index_create.argtypes = [i32, i32, i64, i32, C.POINTER(vp)]
     L.icd_index_destroy.argtypes = [vp]
     L.icd_index_append.argtypes = [vp, vp, i32, vp, i64]
@@ -129,6 +130,12 @@ def check(status: int, what: str = "") -> None:
     if status != 0:
         msg = lib().icd_last_error().decode("utf-8", "replace")
         raise NativeError(f"{what} failed with status {status}: {msg}")
+
+
+def tune(**knobs: int) -> None:
+    """icd_tune: process-wide knobs of the tensor-core scan, e.g. tune(scan_sample=4)."""
+    for key, value in knobs.items():
+        check(lib().icd_tune(key.encode(), int(value)), f"icd_tune({key})")
 
 
 def require_gpu() -> None:

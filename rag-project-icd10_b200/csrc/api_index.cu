@@ -129,9 +129,10 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
     }
   } else {
     if (use_tc) {
-      if (!x->map_valid) {
+      if (!x->map_valid || x->map_gen != tensor_scan_generation()) {
         ICD_TRY(tensor_scan_make_map(x->tmap, x->table, n, x->dim));
         x->map_valid = true;
+        x->map_gen = tensor_scan_generation();
         x->map_rows = n;
       }
       TensorScanArgs a{};
@@ -147,9 +148,35 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
       a.part_id = (int*)x->part_id.ptr;
       a.P = P;
       a.groups_used = &P_used;
-      ICD_TRY(x->gbound.reserve((size_t)B * 4));
-      ICD_CUDA(cudaMemsetAsync(x->gbound.ptr, 0x80, (size_t)B * 4, st));
+      // [B] pruning bounds followed by the zeroed drift-limiter counters (two regions: pre-pass, main)
+      const int prog_ints = tensor_scan_progress_ints();
+      ICD_TRY(x->gbound.reserve(((size_t)B + 2 * prog_ints) * 4));
+      ICD_CUDA(cudaMemsetAsync((int*)x->gbound.ptr + B, 0, (size_t)2 * prog_ints * 4, st));
       a.gbound = (int*)x->gbound.ptr;
+      a.progress = (int*)x->gbound.ptr + B;
+      const int sample = tensor_scan_sample_stride(n);
+      ICD_CUDA(cudaMemsetAsync(x->gbound.ptr, 0x80, (size_t)B * 4, st));
+      if (sample > 1) {
+        // sampling pre-pass: exact top-kc of every `sample`-th row tile; its kc-th best score is a
+        // proven lower bound of the final kc-th best, so the main scan admits only rows that reach
+        // it (about kc * sample rows per query instead of every row of each list's warm-up)
+        a.tile_stride = sample;
+        ICD_TRY(launch_tensor_scan(a, x->tmap, st));
+        MergeArgs m{};
+        m.part_score = (const float*)x->part_score.ptr;
+        m.part_id = (const int*)x->part_id.ptr;
+        m.B = B;
+        m.P = P_used;
+        m.k_in = kc;
+        m.k_out = kc;
+        m.out_score = (float*)x->cand_score.ptr;
+        m.out_id = (int64_t*)x->cand_id.ptr;
+        m.row_offset = 0;
+        m.bound_key_out = (int*)x->gbound.ptr;
+        ICD_TRY(launch_merge(m, st));
+        a.tile_stride = 1;
+        a.progress += prog_ints;
+      }
       ICD_TRY(launch_tensor_scan(a, x->tmap, st));
     } else {
       const int per = stream_scan_max_queries(scan_f32rows, x->dim);
@@ -256,6 +283,14 @@ extern "C" {
 int icd_version(void) { return 100; }
 const char* icd_last_error(void) { return t_error.c_str(); }
 int64_t icd_launch_count(void) { return g_launches.load(); }
+int icd_tune(const char* key, int value) {
+  ICD_CHECK_ARG(key != nullptr, "key is null");
+  if (tensor_scan_tune(key, value) != ICD_OK) {
+    set_error("icd_tune: unknown key '%s'", key);
+    return ICD_E_ARG;
+  }
+  return ICD_OK;
+}
 int icd_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -73,6 +73,13 @@ __device__ __forceinline__ double level_weight_d(uint8_t level) {
   return level == 1 ? 1.2 : (level == 3 ? 0.8 : 1.0);
 }
 
+// order-preserving float <-> int key (signed int compare == float compare, -0 < +0 harmless)
+__device__ __forceinline__ int float_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
 // ------------------------------------------------------------------ bf16 <-> f32 bit tricks
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }

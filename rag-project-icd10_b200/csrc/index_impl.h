@@ -30,6 +30,7 @@ struct icd_index {
   alignas(128) unsigned char tmap[128];
   bool map_valid = false;
   int64_t map_rows = 0;
+  int map_gen = -1;
   // workspace
   icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage, gbound;
   // stage timing (scan, merge, finalise)

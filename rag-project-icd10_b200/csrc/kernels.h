@@ -40,8 +40,16 @@ struct TensorScanArgs {
   int P;              // partial lists per query the buffers were sized for (>= groups used)
   int* groups_used;   // out: partial lists actually written per query
   int* gbound;        // [B] ints, pre-set to 0x80808080 (a very negative key), or null to disable pruning
+  int* progress;      // [tensor_scan_progress_ints()] zeroed ints for the drift limiter, or null
+  int tile_stride;    // 0/1: scan every row; s > 1: scan every s-th 128-row tile only (sampling pre-pass)
 };
+// stride of the sampling pre-pass for a table of n_rows (0 = no pre-pass)
+int tensor_scan_sample_stride(int64_t n_rows);
+// run-time tuning (icd_tune); the generation moves whenever a knob that shapes the TMA descriptor changes
+int tensor_scan_tune(const char* key, int value);
+int tensor_scan_generation();
 int tensor_scan_max_partials();
+int tensor_scan_progress_ints();
 bool tensor_scan_supported(int dim, int k);
 int launch_tensor_scan(const TensorScanArgs& a, const void* tensor_map_owner, cudaStream_t st);
 // builds (or rebuilds) the TMA descriptor of the table; owner is an opaque 128-byte aligned blob
@@ -56,6 +64,8 @@ struct MergeArgs {
   float* out_score;          // [B, k_out]
   int64_t* out_id;           // [B, k_out] local row + row_offset, -1 = empty
   int64_t row_offset;
+  int* bound_key_out;        // [B] or null: order-preserving key of the k_out-th score (very negative when
+                             // the list holds fewer than k_out rows) -- the admission bound of the main scan
 };
 int launch_merge(const MergeArgs& a, cudaStream_t st);
 

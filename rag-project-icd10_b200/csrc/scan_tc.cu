@@ -33,6 +33,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 //
 // Roofline: HBM for B <~ 200 (one pass over the table per launch), bf16 tensor pipe above.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -45,9 +46,7 @@ namespace icd {
 namespace {
 
 constexpr int BM = 128;  // queries per CTA
-constexpr int BN = 128;  // table rows per accumulator tile
 constexpr int BK = 64;   // bf16 per TMA box row (128 bytes)
-constexpr int kBoxBytes = BN * BK * 2;  // one 128 x 64 bf16 tile: 16 KiB
 constexpr int kMaxStages = 12;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
@@ -68,6 +67,9 @@ struct ScanParams {
   int kbs;       // K blocks (128 x 64 tiles) per stage; divides nkb
   int nacc;      // accumulator buffers (1 or 2) in the TMEM columns behind the query tile
   int acc_col0;  // first accumulator column (== dim / 2 rounded up to 128)
+  int tstride;   // scan every tstride-th row tile only (1 = all rows; > 1 = the sampling pre-pass)
+  int* progress; // [G * T] tiles issued by each CTA's producer (drift limiter), or null
+  int drift;     // a producer may run at most this many tiles ahead of the slowest CTA of its row group
 };
 
 // Private candidate list of one query (thread): kc entries sorted by (score desc, id asc) in
@@ -86,15 +88,11 @@ __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, i
   return ls[(kc - 1) * BM];
 }
 
-// order-preserving float <-> int key (signed int compare == float compare, -0 < +0 harmless)
-__device__ __forceinline__ int float_key(float f) {
-  const int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
-
+// BN = table rows per accumulator tile (MMA N)
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  constexpr int kBoxBytes = BN * BK * 2;  // one BN x 64 bf16 tile
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x / p.T;
@@ -113,7 +111,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   // row tiles of this group
-  const int64_t total_tiles = (p.n_rows + BN - 1) / BN;
+  const int64_t total_tiles = ((p.n_rows + BN - 1) / BN + p.tstride - 1) / p.tstride;
   const int64_t t0 = total_tiles * g / p.G;
   const int64_t t1 = total_tiles * (g + 1) / p.G;
 
@@ -178,11 +176,33 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (ptx::elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t t = t0; t < t1; ++t) {
-        const int row = (int)(t * BN);
+    // Drift limiter: the T CTAs of a row group stream the same rows; left alone they drift apart
+    // by more than the L2 holds and every one of them re-reads the rows from HBM (ncu, B=1024:
+    // 3.0x the algorithmic DRAM bytes).  Each producer publishes the tile it is about to issue
+    // and does not run more than `drift` tiles ahead of the slowest CTA of its group, so one
+    // HBM read serves the whole group out of L2.  (All CTAs are co-resident: grid <= 148, 1/SM.)
+    int* prog = p.progress ? p.progress + (size_t)g * p.T : nullptr;
+    const int me = blockIdx.x % p.T;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+      if (prog && (it & 1) == 0) {
+        if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + me), "r"(it) : "memory");
+        for (uint32_t spins = 0; spins < (1u << 16); ++spins) {
+          int v = 0x7fffffff;
+          for (int l = lane; l < p.T; l += 32) {
+            int w;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(w) : "l"(prog + l) : "memory");
+            v = min(v, w);
+          }
+          v = __reduce_min_sync(0xffffffffu, v);
+          if (v + p.drift >= it) break;
+          __nanosleep(256);
+        }
+      }
+      if (lane == 0) {
+        const int row = (int)(t * p.tstride * BN);
         for (int kb = 0; kb < p.nkb; kb += p.kbs) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
@@ -194,7 +214,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           }
         }
       }
+      __syncwarp();
     }
+    if (prog && lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + me), "r"(0x7fffffff) : "memory");
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
@@ -263,7 +285,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
 
-      const int64_t row0 = t * BN;
+      const int64_t row0 = t * p.tstride * BN;
       const int valid = (int)min((int64_t)BN, p.n_rows - row0);
 #pragma unroll
       for (int c32 = 0; c32 < BN / 32; ++c32) {
@@ -318,8 +340,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   }
 }
 
-size_t smem_bytes(int nst, int kbs, int kc) {
-  return (size_t)nst * kbs * kBoxBytes + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
+size_t smem_bytes(int bn, int nst, int kbs, int kc) {
+  return (size_t)nst * kbs * (bn * BK * 2) + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
 }
 
 }  // namespace
@@ -383,7 +405,53 @@ int make_tmap_bf16_3d(void* map128, const void* base, uint64_t d0, uint64_t d1, 
   return ICD_OK;
 }
 
+// tuning knobs: defaults from the environment (ICD_SCAN_BN = 64 | 128, ICD_SCAN_DRIFT = tiles, 0 = limiter
+// off, ICD_SCAN_TMAX = query tiles sharing one row stream per launch, ICD_SCAN_KBS = K blocks per stage,
+// ICD_SCAN_SAMPLE = pre-pass stride, 0 = off, -1 = by table size); icd_tune() overrides them at run time.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+struct Tunables {
+  int bn, drift, tmax, kbs, sample, gen;
+  Tunables() {
+    bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
+    drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
+    tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 8)));
+    kbs = std::min(3, std::max(1, env_int("ICD_SCAN_KBS", 2)));
+    sample = env_int("ICD_SCAN_SAMPLE", -1);
+    gen = 0;
+  }
+};
+static Tunables& tun() {
+  static Tunables t;
+  return t;
+}
+static int scan_bn() { return tun().bn; }
+static int scan_drift() { return tun().drift; }
+static int scan_tmax() { return tun().tmax; }
+
+int tensor_scan_tune(const char* key, int value) {
+  Tunables& t = tun();
+  if (!strcmp(key, "scan_bn")) t.bn = value == 64 ? 64 : 128;
+  else if (!strcmp(key, "scan_drift")) t.drift = std::max(0, value);
+  else if (!strcmp(key, "scan_tmax")) t.tmax = std::min(32, std::max(1, value));
+  else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(3, std::max(1, value));
+  else if (!strcmp(key, "scan_sample")) t.sample = value;
+  else return ICD_E_ARG;
+  ++t.gen;  // tensor maps depend on bn / kbs: indexes rebuild theirs when the generation moves
+  return ICD_OK;
+}
+int tensor_scan_generation() { return tun().gen; }
+
 int tensor_scan_max_partials() { return kSMs; }
+int tensor_scan_sample_stride(int64_t n_rows) {
+  const int forced = tun().sample;
+  if (forced >= 0) return forced <= 1 ? 0 : forced;
+  // calibrated on 10 M and 100 M rows (profiles/r01_scan_experiments.md): the optimum is broad around 256
+  return n_rows >= (2 << 20) ? 256 : (n_rows >= (1 << 19) ? 64 : 0);
+}
+int tensor_scan_progress_ints() { return 64 * kSMs; }
 
 bool tensor_scan_supported(int dim, int k) {
   return dim % BK == 0 && dim >= BK && dim <= 768 && k >= 1 && k <= ICD_MAX_K;
@@ -391,25 +459,27 @@ bool tensor_scan_supported(int dim, int k) {
 
 static int stage_kblocks(int dim) {
   const int nkb = dim / BK;
-  for (int kbs = 2; kbs > 1; --kbs)
+  const int want = tun().kbs;
+  for (int kbs = std::min(want, nkb); kbs > 1; --kbs)
     if (nkb % kbs == 0) return kbs;
   return 1;
 }
 
 int tensor_scan_make_map(void* map128, const void* table, int64_t n_rows, int dim) {
   // 3-D view {64 elements, rows, K blocks}: strides {dim*2 bytes, 128 bytes}
-  return make_tmap_bf16_3d(map128, table, BK, (uint64_t)n_rows, (uint64_t)(dim / BK), (uint64_t)dim * 2, BK * 2, BK, BN,
-                           (uint32_t)stage_kblocks(dim));
+  return make_tmap_bf16_3d(map128, table, BK, (uint64_t)n_rows, (uint64_t)(dim / BK), (uint64_t)dim * 2, BK * 2, BK,
+                           (uint32_t)scan_bn(), (uint32_t)stage_kblocks(dim));
 }
 
-int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
-  if (!tensor_scan_supported(a.dim, a.k)) {
-    set_error("tensor scan: unsupported dim=%d k=%d", a.dim, a.k);
-    return ICD_E_UNSUPPORTED;
-  }
+template <int BN>
+static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
   const int T_total = (a.B + BM - 1) / BM;
-  const int64_t total_tiles = (a.n_rows + BN - 1) / BN;
-  const int T_launch = std::min(T_total, kSMs);
+  const int tstride = std::max(1, a.tile_stride);
+  const int64_t total_tiles = ((a.n_rows + BN - 1) / BN + tstride - 1) / tstride;
+  // query tiles per launch: as equal as possible over ceil(T_total / tmax) launches, so that every
+  // launch fills the SMs (G * T_launch <= 148) and at most tmax CTAs share one row stream
+  const int n_launch = (T_total + scan_tmax() - 1) / scan_tmax();
+  const int T_launch = (T_total + n_launch - 1) / n_launch;
   int G = std::max(1, kSMs / T_launch);
   G = (int)std::min<int64_t>(G, total_tiles);
   G = std::min(G, a.P);
@@ -418,16 +488,17 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
   // pipeline depth from the shared memory left after the per-thread lists
   const int kbs = stage_kblocks(a.dim);
   int nst = kMaxStages;
-  while (nst > 2 && smem_bytes(nst, kbs, a.k) > (size_t)kSmemLimit) --nst;
-  if (smem_bytes(nst, kbs, a.k) > (size_t)kSmemLimit) {
+  while (nst > 2 && smem_bytes(BN, nst, kbs, a.k) > (size_t)kSmemLimit) --nst;
+  if (smem_bytes(BN, nst, kbs, a.k) > (size_t)kSmemLimit) {
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
-  const size_t smem = smem_bytes(nst, kbs, a.k);
-  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  const size_t smem = smem_bytes(BN, nst, kbs, a.k);
+  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CUtensorMap tmap;
   memcpy(&tmap, map128, sizeof(CUtensorMap));
-  for (int qt0 = 0; qt0 < T_total; qt0 += T_launch) {
+  int launch = 0;
+  for (int qt0 = 0; qt0 < T_total; qt0 += T_launch, ++launch) {
     ScanParams p{};
     p.levels = a.levels;
     p.q = reinterpret_cast<const __nv_bfloat16*>(a.q_bf16);
@@ -447,11 +518,22 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
     p.kbs = kbs;
     p.acc_col0 = ((a.dim / 2 + 127) / 128) * 128;
     p.nacc = (kTmemCols - p.acc_col0) / BN >= 2 ? 2 : 1;
-    scan_tc_kernel<<<G * p.T, kThreads, smem, st>>>(tmap, p);
+    p.tstride = tstride;
+    p.drift = scan_drift();
+    p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64) ? a.progress + (size_t)launch * kSMs : nullptr;
+    scan_tc_kernel<BN><<<G * p.T, kThreads, smem, st>>>(tmap, p);
     count_launch();
     ICD_CUDA(cudaGetLastError());
   }
   return ICD_OK;
+}
+
+int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
+  if (!tensor_scan_supported(a.dim, a.k)) {
+    set_error("tensor scan: unsupported dim=%d k=%d", a.dim, a.k);
+    return ICD_E_UNSUPPORTED;
+  }
+  return scan_bn() == 64 ? launch_tensor_scan_bn<64>(a, map128, st) : launch_tensor_scan_bn<128>(a, map128, st);
 }
 
 }  // namespace icd

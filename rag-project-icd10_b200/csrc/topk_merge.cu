@@ -16,7 +16,7 @@ constexpr int kMaxP = 1024;
 __global__ void __launch_bounds__(kMergeWarps * 32)
 merge_kernel(const float* __restrict__ part_score, const int* __restrict__ part_id, int B, int P,
              int k_in, int k_out, float* __restrict__ out_score, int64_t* __restrict__ out_id,
-             int64_t row_offset) {
+             int64_t row_offset, int* __restrict__ bound_key_out) {
   __shared__ unsigned char heads[kMergeWarps][kMaxP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kMergeWarps + warp;
@@ -66,6 +66,7 @@ merge_kernel(const float* __restrict__ part_score, const int* __restrict__ part_
     if (lane == 0) {
       out_score[(size_t)b * k_out + j] = (wl < 0) ? -INFINITY : ws;
       out_id[(size_t)b * k_out + j] = (wl < 0) ? -1 : (int64_t)wi + row_offset;
+      if (bound_key_out && j == k_out - 1) bound_key_out[b] = (wl < 0) ? (int)0x80808080 : float_key(ws);
     }
     if (wl >= 0 && (wl & 31) == lane) {
       hd[wl] = hd[wl] + 1;
@@ -276,7 +277,7 @@ int launch_merge(const MergeArgs& a, cudaStream_t st) {
   }
   const int grid = (a.B + kMergeWarps - 1) / kMergeWarps;
   merge_kernel<<<grid, kMergeWarps * 32, 0, st>>>(a.part_score, a.part_id, a.B, a.P, a.k_in, a.k_out,
-                                                 a.out_score, a.out_id, a.row_offset);
+                                                 a.out_score, a.out_id, a.row_offset, a.bound_key_out);
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;

@@ -210,3 +210,43 @@ def test_full_size_properties(pkg, native):
     s = q.float() @ t[sample].float().T
     assert torch.all(s <= raw2[:, :1] + 1e-6)
     idx.close()
+
+
+@pytest.mark.parametrize("knobs", [dict(scan_sample=4), dict(scan_sample=3, scan_drift=1), dict(scan_sample=0, scan_drift=0),
+                                   dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=3)])
+@pytest.mark.parametrize("weight_mode", [2, 1])
+def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
+    """The sampling pre-pass (admission bound from every s-th row tile), the drift limiter and the
+    launch shaping are performance devices: with any setting the tensor scan returns the oracle's
+    top-k.  Forced on here at sizes the oracle finishes in seconds (by default the pre-pass
+    only runs on tables of >= 2 M rows)."""
+    n, B, k, dim = 60000, 300, 10, 768
+    corpus = _corpus(n, dim, seed=21)
+    # duplicate rows make exact score ties across row tiles: the bound must admit equal scores
+    corpus[1000:1064] = corpus[50000:50064]
+    levels = _levels(n, seed=22)
+    q = _corpus(B, dim, seed=23)
+    q[:32] = corpus[50000:50032]
+    idx = _index(pkg, corpus, levels)
+    try:
+        native.tune(**knobs)
+        score, raw, ids = idx.search(q, k, weight_mode=weight_mode, path=native.PATH_TENSOR)
+    finally:
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2)
+    if weight_mode == native.WEIGHT_PRE:
+        w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
+        full = (q @ corpus.T) * w[None, :]
+        for b in range(B):
+            ref = np.lexsort((np.arange(n), -full[b].astype(np.float64)))[:k]
+            got_w = full[b][ids[b]]
+            assert len(set(ids[b].tolist())) == k
+            assert np.all(np.abs(got_w - full[b][ref]) <= 1e-3), (b, ids[b], ref)
+            np.testing.assert_allclose(score[b], got_w, atol=3e-6)
+    else:
+        ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+        swaps = check_topk(ids, raw, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+        assert swaps <= B * k // 50
+        # the planted duplicates: both copies of the row come back, lower id first
+        for b in range(32):
+            assert ids[b, 0] == 1000 + b and ids[b, 1] == 50000 + b, (b, ids[b, :3])
+    idx.close()
