@@ -15,6 +15,8 @@
 //     intermediate.dense.weight [I, H], .bias [I]
 //     output.dense.weight [H, I], .bias [H]
 //     output.LayerNorm.weight / .bias                            [H] [H]
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -51,6 +53,7 @@ struct icd_encoder {
   alignas(128) unsigned char m_h1[128];
   alignas(128) unsigned char m_ctx[128];
   alignas(128) unsigned char m_f[128];
+  alignas(128) unsigned char m_qkv[128];
   int32_t *ids = nullptr, *lens = nullptr;
   int ids_cap = 0, lens_cap = 0;
   void* out_stage = nullptr;
@@ -106,6 +109,7 @@ static int reserve_tokens(icd_encoder* e, int max_tokens) {
   ICD_TRY(gemm_make_map_a(e->m_h1, e->h1, M, H));
   ICD_TRY(gemm_make_map_a(e->m_ctx, e->ctx, M, H));
   ICD_TRY(gemm_make_map_a(e->m_f, e->f, M, I));
+  ICD_TRY(attention_make_map(e->m_qkv, e->qkv, M));
   e->max_tokens = M;
   return ICD_OK;
 }
@@ -262,6 +266,7 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
     d_out = e->out_stage;
   }
 
+  static const bool cuda_core_attention = getenv("ICD_ATTN_CUDA_CORE") != nullptr;  // A/B timing only
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
   for (size_t l = 0; l < e->layers.size(); ++l) {
     LayerW* L = e->layers[l];
@@ -269,7 +274,10 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
     // qkv = h Wqkv^T + b
     g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->qkv, M, 3 * H, H, EPI_BIAS};
     ICD_TRY(launch_gemm_tc(g, st));
-    ICD_TRY(launch_attention(e->qkv, d_lens, B, S, e->ctx, st));
+    if (cuda_core_attention)
+      ICD_TRY(launch_attention(e->qkv, d_lens, B, S, e->ctx, st));
+    else
+      ICD_TRY(launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, st));
     // t = ctx Wo^T + bo + h ; h1 = LN(t)
     g = GemmArgs{e->m_ctx, L->m_o, L->bo, e->h, e->t, M, H, H, EPI_BIAS_RESIDUAL};
     ICD_TRY(launch_gemm_tc(g, st));
