@@ -41,6 +41,17 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def _ncu_traffic(kernel, rows_local, batch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    exact workload (profiles/ncu_traffic.json), or (None, None) when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            ent = json.load(fh).get(f"{kernel}:{rows_local}:{batch}")
+        return (ent["bytes"], ent["capture"]) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -352,6 +363,26 @@ def main():
     torch.cuda.synchronize(dev)
     same = bool(torch.equal(o_id.cpu(), h_id))
 
+    # ------------------------------------------------ encoder (BASELINE configs[2]), data-parallel replicas
+    enc = None
+    if not args.no_encoder:
+        try:
+            enc_bench = importlib.import_module("rag-project-icd10_b200.engine.encoder").bench_encoder
+            enc = enc_bench(dev, peaks, barrier=barrier)
+            ok = 1.0
+        except Exception as e:  # encoder line is auxiliary; the headline must still print
+            enc = {"error": repr(e)[:200]}
+            ok = 0.0
+        t = torch.tensor([enc.get("ms_per_batch", 0.0), -ok], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if float(t[1]) == -1.0 and "error" not in enc:
+            ms = float(t[0])  # max over ranks; every rank encodes its own batch (weak scaling, no exchange)
+            enc.update({"ms_per_batch": ms, "value": world * enc["batch"] / (ms * 1e-3), "n_gpus": world,
+                        "tflops": world * enc["flops_per_batch"] / (ms * 1e-3) / 1e12,
+                        "frac_of_bf16_sustained": enc["flops_per_batch"] / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                        "scaling": "weak (one batch per GPU, replicas, no collective)"})
+
     if rank == 0:
         flops = 2.0 * B * rows_local * DIM                     # per scan launch (per GPU)
         bytes_alg = rows_local * DIM * 2 + B * DIM * 2 + B * k * 16
@@ -363,8 +394,9 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": bytes_alg / scan_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["traffic"] = None
         roof["kernel"] = "scan_tc_kernel" if tm["launches"] and B > 4 else "scan_stream_kernel"
+        roof["traffic"], roof["traffic_source"] = _ncu_traffic(roof["kernel"], rows_local, B)
+        roof["algorithmic_bytes"] = bytes_alg
         roof["kernel_us"] = scan_us_max
         roof["peak_source"] = peaks["source"] + (" (sustained)" if tensor_bound else "")
         roof["hbm_gbs_of_scan"] = bytes_alg / scan_s / 1e9
@@ -387,12 +419,8 @@ def main():
                 "cores": os.cpu_count(), "kind": "port",
                 "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows (numpy fp32 GEMM + argpartition top-k, "
                           f"oracle/search.py::fast_topk), extrapolated linearly in rows to {rows_total}"}
-        if not args.no_encoder:
-            try:
-                enc_bench = importlib.import_module("rag-project-icd10_b200.engine.encoder").bench_encoder
-                line["encoder"] = enc_bench(dev, peaks)
-            except Exception as e:  # encoder line is auxiliary; the headline must still print
-                line["encoder"] = {"error": repr(e)[:200]}
+        if enc is not None:
+            line["encoder"] = enc
         emit(line)
     if world > 1:
         dist.barrier()

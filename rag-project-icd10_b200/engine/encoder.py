@@ -192,7 +192,7 @@ def smoke() -> None:
     eng.close()
 
 
-def bench_encoder(dev, peaks, batch: int = 4096, seq: int = 64, steps: int = 3, warmup: int = 2):
+def bench_encoder(dev, peaks, batch: int = 4096, seq: int = 64, steps: int = 3, warmup: int = 3, barrier=None):
     """BASELINE configs[2]: encoder throughput at S=64, B=4096 on synthetic ids, random-init
     weights of the text2vec-base-chinese architecture.  Returns the `encoder` object of bench.py."""
     import torch
@@ -207,18 +207,22 @@ def bench_encoder(dev, peaks, batch: int = 4096, seq: int = 64, steps: int = 3, 
     for _ in range(warmup):
         eng.forward_ids(ids, lens, out=out, stream=stream.cuda_stream, sync=False)
     torch.cuda.synchronize(dev)
+    if barrier is not None:
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
         eng.forward_ids(ids, lens, out=out, stream=stream.cuda_stream, sync=False)
     e1.record(stream)
     torch.cuda.synchronize(dev)
+    if barrier is not None:
+        barrier()
     ms = e0.elapsed_time(e1) / steps
     flops = batch * seq * 12 * (2 * (4 * 768 * 768 + 2 * 768 * 3072) + 4 * seq * 768)
     tf = flops / (ms * 1e-3) / 1e12
     norm = float(out.norm(dim=1).mean())
     eng.close()
     return {"metric": "text2vec sentences/sec", "value": batch / (ms * 1e-3), "unit": "sentences/s",
-            "ms_per_batch": ms, "batch": batch, "seq_len": seq, "layers": 12, "dtype": "bf16",
+            "ms_per_batch": ms, "flops_per_batch": flops, "batch": batch, "seq_len": seq, "layers": 12, "dtype": "bf16",
             "tflops": tf, "frac_of_bf16_sustained": tf / peaks["bf16_tflops_sustained"], "mean_norm": norm,
             "data": "synthetic ids, random-init weights"}
