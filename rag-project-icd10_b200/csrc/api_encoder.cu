@@ -54,6 +54,8 @@ struct icd_encoder {
   alignas(128) unsigned char m_ctx[128];
   alignas(128) unsigned char m_f[128];
   alignas(128) unsigned char m_qkv[128];
+  alignas(128) unsigned char m_t[128];        // GEMM output maps (box 128 x 64)
+  alignas(128) unsigned char m_qkv_out[128];
   int32_t *ids = nullptr, *lens = nullptr;
   int ids_cap = 0, lens_cap = 0;
   void* out_stage = nullptr;
@@ -110,6 +112,8 @@ static int reserve_tokens(icd_encoder* e, int max_tokens) {
   ICD_TRY(gemm_make_map_a(e->m_ctx, e->ctx, M, H));
   ICD_TRY(gemm_make_map_a(e->m_f, e->f, M, I));
   ICD_TRY(attention_make_map(e->m_qkv, e->qkv, M));
+  ICD_TRY(gemm_make_map_out(e->m_t, e->t, M, H));
+  ICD_TRY(gemm_make_map_out(e->m_qkv_out, e->qkv, M, 3 * H));
   e->max_tokens = M;
   return ICD_OK;
 }
@@ -272,21 +276,21 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
     LayerW* L = e->layers[l];
     GemmArgs g{};
     // qkv = h Wqkv^T + b
-    g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->qkv, M, 3 * H, H, EPI_BIAS};
+    g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->m_qkv_out, M, 3 * H, H, EPI_BIAS};
     ICD_TRY(launch_gemm_tc(g, st));
     if (cuda_core_attention)
       ICD_TRY(launch_attention(e->qkv, d_lens, B, S, e->ctx, st));
     else
       ICD_TRY(launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, st));
     // t = ctx Wo^T + bo + h ; h1 = LN(t)
-    g = GemmArgs{e->m_ctx, L->m_o, L->bo, e->h, e->t, M, H, H, EPI_BIAS_RESIDUAL};
+    g = GemmArgs{e->m_ctx, L->m_o, L->bo, e->m_h, e->m_t, M, H, H, EPI_BIAS_RESIDUAL};
     ICD_TRY(launch_gemm_tc(g, st));
     ICD_TRY(launch_layernorm(e->t, M, L->ln1g, L->ln1b, eps, e->h1, st));
     // f = gelu(h1 W1^T + b1)
-    g = GemmArgs{e->m_h1, L->m_1, L->b1, nullptr, e->f, M, I, H, EPI_BIAS_GELU};
+    g = GemmArgs{e->m_h1, L->m_1, L->b1, nullptr, e->m_f, M, I, H, EPI_BIAS_GELU};
     ICD_TRY(launch_gemm_tc(g, st));
     // t = f W2^T + b2 + h1 ; h = LN(t)
-    g = GemmArgs{e->m_f, L->m_2, L->b2, e->h1, e->t, M, H, I, EPI_BIAS_RESIDUAL};
+    g = GemmArgs{e->m_f, L->m_2, L->b2, e->m_h1, e->m_t, M, H, I, EPI_BIAS_RESIDUAL};
     ICD_TRY(launch_gemm_tc(g, st));
     ICD_TRY(launch_layernorm(e->t, M, L->ln2g, L->ln2b, eps, e->h, st));
   }

@@ -12,8 +12,8 @@ struct GemmArgs {
   const void* tmap_a;  // 128-byte CUtensorMap of A (box 128 x 64, SWIZZLE_128B)
   const void* tmap_b;  // CUtensorMap of W (box 256 x 64, SWIZZLE_128B)
   const float* bias;   // [N] fp32
-  const void* residual;  // [M,N] bf16 (EPI_BIAS_RESIDUAL) or null
-  void* out;             // [M,N] bf16
+  const void* tmap_res;  // CUtensorMap of the residual [rows,N] bf16 (box 128 x 64; EPI_BIAS_RESIDUAL) or null
+  const void* tmap_out;  // CUtensorMap of out [rows,N] bf16 (box 128 x 64); rows is a multiple of 128 >= M
   int M, N, K;
   int epi;
 };
@@ -21,6 +21,7 @@ int gemm_tile_n();
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);
 int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K);
 int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K);
+int gemm_make_map_out(void* map128, const void* base, int64_t rows, int N);
 
 // ---- encoder_kernels.cu
 // h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0])

@@ -9,6 +9,15 @@
 // ring; tcgen05.mma (M=128, N=256, K=16) accumulates in TMEM, double-buffered (2 x 256
 // columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
+// Epilogue: thread == TMEM lane == output row, so a direct global store would scatter 16-byte
+// pieces over 32 rows per instruction (ncu r01b: the K=768 GEMMs were bound by exactly that:
+// 49 % / 68 % of peak for the O and QKV projections against 89 % for K=3072).  Instead each
+// column-half group of 4 warps owns one 128 x 64 staging box in shared memory (128-byte
+// swizzle, conflict-free 16-byte accesses), converts its accumulators into it and one thread
+// hands the box to TMA (cp.async.bulk.tensor store: full 128-byte lines to L2).  The residual
+// of the O / FFN-down projections arrives the same way: a TMA load of the matching box of the
+// residual stream into the staging box, prefetched as soon as the previous store has drained.
+//
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4).
 //
@@ -34,15 +43,21 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kBoxCols = 64;                    // staging box: 128 rows x 64 bf16 (128-byte rows)
+constexpr int kBoxBytes = BM * kBoxCols * 2;    // 16 KiB
+constexpr int kBoxesPerHalf = (BN / 2) / kBoxCols;  // 2
+constexpr int kSmemBytes = kStages * kStageBytes + 2 * kBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmParams {
-  const float* bias;               // [N]
-  const __nv_bfloat16* residual;   // [M, N] or null
-  __nv_bfloat16* out;              // [M, N]
+  const float* bias;  // [N]
   int M, N, K;
-  int epi;                         // GemmEpilogue
+  int epi;            // GemmEpilogue
 };
+
+// named barrier over the 128 threads of one column-half epilogue group (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int half) {
+  asm volatile("bar.sync %0, 128;" ::"r"(half + 1) : "memory");
+}
 
 // HF "gelu" = x * Phi(x) with Phi(x) = 0.5 * (1 + erf(x / sqrt(2))).  The epilogue of the FFN-up GEMM
 // evaluates 32 K of these per 128 x 256 tile while the next tile's MMAs run, so it has to fit ~20 issue
@@ -77,17 +92,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                const GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  unsigned char* stage_c = smem + kStages * kStageBytes;  // [2 halves][128 x 64 bf16], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + 2 * kBoxBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tfull_bar = bars + 2 * kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;  // [2] residual box landed (one per column half)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int m_tiles = (p.M + BM - 1) / BM;
   const int n_tiles = p.N / BN;
@@ -97,6 +115,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    ptx::prefetch_tmap(&tmap_out);
+    if (p.epi == EPI_BIAS_RESIDUAL) ptx::prefetch_tmap(&tmap_res);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
@@ -104,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
       ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), kEpiWarps);
+      ptx::mbar_init(ptx::smem_u32(&res_bar[b]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -167,37 +188,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // epilogue: thread = row of the tile (TMEM lane), this warp covers 128 of the 256 columns
+    // epilogue: thread = row of the tile (TMEM lane); the 4 warps of a column half share one staging box
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row_in_tile = 32 * quarter + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
+    const bool leader = (warp == 2 + 4 * half) && lane == 0;  // issues this group's TMA traffic
+    const bool with_res = p.epi == EPI_BIAS_RESIDUAL;
+    unsigned char* box = stage_c + half * kBoxBytes;
+    const uint32_t box_u32 = ptx::smem_u32(box);
+    // this thread's row inside the box: 128 bytes, 16-byte chunk c lives at chunk (c ^ (row & 7))
+    unsigned char* my_row = box + row_in_tile * 128;
+    const int sw = row_in_tile & 7;
+    const uint32_t rbar = ptx::smem_u32(&res_bar[half]);
+    uint32_t res_phase = 0;
+    if (with_res && leader && (int)blockIdx.x < tiles) {
+      const int m0 = ((int)blockIdx.x / n_tiles) * BM, n0 = ((int)blockIdx.x % n_tiles) * BN;
+      ptx::mbar_expect_tx(rbar, kBoxBytes);
+      ptx::tma_load_2d(box_u32, &tmap_res, rbar, n0 + half * (BN / 2), m0);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-      const int row = m0 + row_in_tile;
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c32 = 0; c32 < (BN / 2) / 32; ++c32) {
-        const int col0 = half * (BN / 2) + c32 * 32;  // column within the tile
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(buf * BN + col0), r);
-        ptx::tmem_ld_wait();
-        if (c32 == (BN / 2) / 32 - 1) {
-          // last read of this accumulator buffer by this warp: hand it back to the MMA warp
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+      for (int bx = 0; bx < kBoxesPerHalf; ++bx) {
+        const int col0 = half * (BN / 2) + bx * kBoxCols;  // first column of this box within the tile
+        // the staging box is free once the leader has seen the previous store drain (it arrives here after that)
+        group_sync(half);
+        if (with_res) {
+          ptx::mbar_wait(rbar, res_phase);
+          res_phase ^= 1;
         }
-        if (row < p.M) {
-          const int gcol = n0 + col0;
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + gcol);
-          __nv_bfloat16* orow = p.out + (size_t)row * p.N + gcol;
-          const uint4* res4 = p.residual ? reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.N + gcol) : nullptr;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {  // 8 columns per 16-byte store
+        for (int c32 = 0; c32 < kBoxCols / 32; ++c32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + (uint32_t)(buf * BN + col0 + c32 * 32), r);
+          ptx::tmem_ld_wait();
+          if (bx == kBoxesPerHalf - 1 && c32 == kBoxCols / 32 - 1) {
+            // last read of this accumulator buffer by this warp: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+          }
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0 + c32 * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {  // 8 columns per 16-byte chunk
             float x[8];
             const float4 b0 = bias4[2 * v], b1 = bias4[2 * v + 1];
             x[0] = __uint_as_float(r[8 * v + 0]) + b0.x;
@@ -208,11 +246,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             x[5] = __uint_as_float(r[8 * v + 5]) + b1.y;
             x[6] = __uint_as_float(r[8 * v + 6]) + b1.z;
             x[7] = __uint_as_float(r[8 * v + 7]) + b1.w;
+            uint4* slot = reinterpret_cast<uint4*>(my_row + (((c32 * 4 + v) ^ sw) << 4));
             if (p.epi == EPI_BIAS_GELU) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
-            } else if (p.epi == EPI_BIAS_RESIDUAL) {
-              const uint4 rr = res4[v];
+            } else if (with_res) {
+              const uint4 rr = *slot;
               x[0] += bf16lo_to_f32(rr.x);
               x[1] += bf16hi_to_f32(rr.x);
               x[2] += bf16lo_to_f32(rr.y);
@@ -227,11 +266,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             o.y = pack_bf16(x[2], x[3]);
             o.z = pack_bf16(x[4], x[5]);
             o.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(orow + 8 * v) = o;
+            *slot = o;
+          }
+        }
+        // generic-proxy writes -> visible to the async proxy, then one thread hands the box to TMA
+        ptx::fence_proxy_async_smem();
+        group_sync(half);
+        if (leader) {
+          ptx::tma_store_2d(&tmap_out, box_u32, n0 + col0, m0);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read<0>();  // the box may be overwritten from here on
+          if (with_res) {
+            // prefetch the residual of the next box (same tile, or the first box of this CTA's next tile)
+            int nm0 = m0, nc = n0 + col0 + kBoxCols;
+            bool more = true;
+            if (bx == kBoxesPerHalf - 1) {
+              const int nt = tile + gridDim.x;
+              more = nt < tiles;
+              nm0 = (nt / n_tiles) * BM;
+              nc = (nt % n_tiles) * BN + half * (BN / 2);
+            }
+            if (more) {
+              ptx::mbar_expect_tx(rbar, kBoxBytes);
+              ptx::tma_load_2d(box_u32, &tmap_res, rbar, nc, nm0);
+            }
           }
         }
       }
     }
+    if (leader) ptx::tma_store_wait_all();  // global writes complete before the kernel ends
   }
 
   ptx::tc_fence_before();
@@ -252,20 +315,24 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     return ICD_E_ARG;
   }
   ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  CUtensorMap ta, tb;
+  if (!a.tmap_out || (a.epi == EPI_BIAS_RESIDUAL && !a.tmap_res)) {
+    set_error("gemm_tc: missing output / residual tensor map");
+    return ICD_E_ARG;
+  }
+  CUtensorMap ta, tb, tout, tres;
   memcpy(&ta, a.tmap_a, sizeof(ta));
   memcpy(&tb, a.tmap_b, sizeof(tb));
+  memcpy(&tout, a.tmap_out, sizeof(tout));
+  memcpy(&tres, a.tmap_res ? a.tmap_res : a.tmap_out, sizeof(tres));
   GemmParams p{};
   p.bias = a.bias;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
-  p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.M = a.M;
   p.N = a.N;
   p.K = a.K;
   p.epi = a.epi;
   const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
   const int grid = std::min(tiles, kSMs);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, p);
+  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tout, tres, p);
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;
@@ -273,6 +340,11 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
 
 int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K) {
   return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)K, BM, BK, true);
+}
+// output / residual boxes have the shape of an A box (128 rows x 64 columns, SWIZZLE_128B), so a buffer that is
+// also read as the next GEMM's A operand needs only one map
+int gemm_make_map_out(void* map128, const void* base, int64_t rows, int N) {
+  return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)N, BM, kBoxCols, true);
 }
 int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K) {
   return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)K, BN, BK, true);
