@@ -22,6 +22,7 @@
 // warps 2..9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4).
 //
 // Roofline: bf16 tensor pipe; 2*M*N*K flops per launch.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,20 +34,28 @@
 namespace icd {
 namespace {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
+constexpr int BM = 128;  // output rows per CTA (TMEM lanes)
+constexpr int BN = 256;  // output columns per tile (TMEM columns per accumulator buffer)
 constexpr int BK = 64;
-constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;  // 16 KiB
-constexpr int kBBytes = BN * BK * 2;  // 32 KiB
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kMaxStages = 6;
+// NC = CTAs per tile: 1 -> 128 x 256 tiles; 2 -> a CTA pair (cluster of 2, cta_group::2) owns a 256 x 256 tile: each
+// CTA loads its own 128 rows of A and HALF of the W tile (128 of the 256 N rows), the pair's MMAs read both halves,
+// so the L2 -> shared-memory traffic per flop drops by a third (48 -> 32 KiB per CTA per K block)
+template <int NC>
+struct Cfg {
+  static constexpr int kBBytes = (BN / NC) * BK * 2;      // 32 / 16 KiB
+  static constexpr int kStageBytes = kABytes + kBBytes;   // 48 / 32 KiB
+  static constexpr int kStages = NC == 1 ? 4 : 6;         // 192 KiB of stages either way
+};
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
 constexpr int kBoxCols = 64;                    // staging box: 128 rows x 64 bf16 (128-byte rows)
 constexpr int kBoxBytes = BM * kBoxCols * 2;    // 16 KiB
 constexpr int kBoxesPerHalf = (BN / 2) / kBoxCols;  // 2
-constexpr int kSmemBytes = kStages * kStageBytes + 2 * kBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = 4 * (kABytes + BN * BK * 2) + 2 * kBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(Cfg<1>::kStages * Cfg<1>::kStageBytes == Cfg<2>::kStages * Cfg<2>::kStageBytes, "same stage budget");
 
 struct GemmParams {
   const float* bias;  // [N]
@@ -90,6 +99,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int NC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -97,17 +107,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128-byte swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStages = Cfg<NC>::kStages, kStageBytes = Cfg<NC>::kStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* stage_c = smem + kStages * kStageBytes;  // [2 halves][128 x 64 bf16], 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + 2 * kBoxBytes);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tfull_bar = bars + 2 * kStages;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;  // [2] residual box landed (one per column half)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2);
 
-  const int m_tiles = (p.M + BM - 1) / BM;
+  // tile walk: a tile is BM * NC rows x BN columns; `unit` = CTA (NC = 1) or CTA pair (NC = 2)
+  const uint32_t rank = NC == 2 ? ptx::cluster_ctarank() : 0u;  // 0 = leader of the pair (issues the MMAs)
+  const int unit = (int)blockIdx.x / NC, units = (int)gridDim.x / NC;
+  const int m_tiles = (p.M + BM * NC - 1) / (BM * NC);
   const int n_tiles = p.N / BN;
   const int tiles = m_tiles * n_tiles;
   const int nkb = p.K / BK;
@@ -123,17 +137,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
-      ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), kEpiWarps);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), kEpiWarps * NC);  // the epilogue warps of every CTA of the tile
       ptx::mbar_init(ptx::smem_u32(&res_bar[b]), 1);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_holder), kTmemCols);
-    ptx::tmem_relinquish();
+    if (NC == 2) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_holder), kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_holder), kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NC == 2) ptx::cluster_sync(); else __syncthreads();  // barriers of BOTH CTAs are initialised from here on
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -141,15 +160,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      for (int tile = unit; tile < tiles; tile += units) {
+        const int m0 = (tile / n_tiles) * (BM * NC) + (int)rank * BM;          // this CTA's rows of A
+        const int nb0 = (tile % n_tiles) * BN + (int)rank * (BN / NC);       // this CTA's share of the W tile
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-          ptx::mbar_expect_tx(fb, kStageBytes);
           unsigned char* sa = smem + (size_t)stage * kStageBytes;
-          ptx::tma_load_2d(ptx::smem_u32(sa), &tmap_a, fb, kb * BK, m0);
-          ptx::tma_load_2d(ptx::smem_u32(sa + kABytes), &tmap_b, fb, kb * BK, n0);
+          if (NC == 1) {
+            const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+            ptx::mbar_expect_tx(fb, kStageBytes);
+            ptx::tma_load_2d(ptx::smem_u32(sa), &tmap_a, fb, kb * BK, m0);
+            ptx::tma_load_2d(ptx::smem_u32(sa + kABytes), &tmap_b, fb, kb * BK, nb0);
+          } else {
+            // both CTAs' bytes are counted on the LEADER's barrier (only its MMA thread waits for the stage)
+            if (rank == 0) ptx::mbar_expect_tx(ptx::smem_u32(&full_bar[stage]), 2 * kStageBytes);
+            const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            ptx::tma_load_2d_pair(ptx::smem_u32(sa), &tmap_a, fb, kb * BK, m0);
+            ptx::tma_load_2d_pair(ptx::smem_u32(sa + kABytes), &tmap_b, fb, kb * BK, nb0);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -158,12 +186,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * NC, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int tile = unit; tile < tiles; tile += units, ++it) {
         const int buf = it & 1;
         ptx::mbar_wait(ptx::smem_u32(&tempty_bar[buf]), ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
@@ -175,16 +203,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k4 = 0; k4 < BK / 16; ++k4) {
-            ptx::mma_ss(d_tmem, ptx::make_desc_k128(sa + k4 * 32), ptx::make_desc_k128(sb + k4 * 32), idesc,
-                        (kb | k4) ? 1u : 0u);
+            if (NC == 1)
+              ptx::mma_ss(d_tmem, ptx::make_desc_k128(sa + k4 * 32), ptx::make_desc_k128(sb + k4 * 32), idesc,
+                          (kb | k4) ? 1u : 0u);
+            else
+              ptx::mma_ss_pair(d_tmem, ptx::make_desc_k128(sa + k4 * 32), ptx::make_desc_k128(sb + k4 * 32), idesc,
+                               (kb | k4) ? 1u : 0u);
           }
-          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));
+          // frees the stage in both CTAs when the MMAs retire
+          if (NC == 1) ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));
+          else ptx::tc_commit_pair(ptx::smem_u32(&empty_bar[stage]), 3);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));
+        if (NC == 1) ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));
+        else ptx::tc_commit_pair(ptx::smem_u32(&tfull_bar[buf]), 3);  // accumulator halves ready in both CTAs
       }
     }
   } else {
@@ -202,15 +237,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int sw = row_in_tile & 7;
     const uint32_t rbar = ptx::smem_u32(&res_bar[half]);
     uint32_t res_phase = 0;
-    if (with_res && leader && (int)blockIdx.x < tiles) {
-      const int m0 = ((int)blockIdx.x / n_tiles) * BM, n0 = ((int)blockIdx.x % n_tiles) * BN;
+    if (with_res && leader && unit < tiles) {
+      const int m0 = (unit / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (unit % n_tiles) * BN;
       ptx::mbar_expect_tx(rbar, kBoxBytes);
       ptx::tma_load_2d(box_u32, &tmap_res, rbar, n0 + half * (BN / 2), m0);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < tiles; tile += units, ++it) {
       const int buf = it & 1;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (tile % n_tiles) * BN;
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -231,7 +266,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // last read of this accumulator buffer by this warp: hand it back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+            if (lane == 0) {
+              if (NC == 1) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+              else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[buf]), 0));  // the leader's barrier
+            }
           }
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0 + c32 * 32);
 #pragma unroll
@@ -281,9 +319,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int nm0 = m0, nc = n0 + col0 + kBoxCols;
             bool more = true;
             if (bx == kBoxesPerHalf - 1) {
-              const int nt = tile + gridDim.x;
+              const int nt = tile + units;
               more = nt < tiles;
-              nm0 = (nt / n_tiles) * BM;
+              nm0 = (nt / n_tiles) * (BM * NC) + (int)rank * BM;
               nc = (nt % n_tiles) * BN + half * (BN / 2);
             }
             if (more) {
@@ -298,10 +336,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may leave (or free its TMEM) while the other can still signal its barriers
+  if (NC == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (NC == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -309,12 +349,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 int gemm_tile_n() { return BN; }
 
+// CTA pairs by default; ICD_GEMM_PAIR=0 selects the single-CTA kernel (A/B timing, and the fallback when the
+// device cannot co-schedule clusters of 2)
+static int pair_mode() {
+  static const int mode = [] {
+    const char* v = getenv("ICD_GEMM_PAIR");
+    return (v && *v) ? (atoi(v) != 0 ? 2 : 1) : 2;
+  }();
+  return mode;
+}
+
+template <int NC>
+static int launch_nc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
+                     const GemmParams& p, cudaStream_t st) {
+  ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int tiles = ((p.M + BM * NC - 1) / (BM * NC)) * (p.N / BN);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int units = kSMs / NC;
+  if (NC == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent kernel: as many pairs as the device can keep resident at once (a TPC with one SM fused off
+    // cannot host a pair)
+    static int resident = 0;
+    if (resident == 0) {
+      cfg.gridDim = dim3(kSMs);
+      int n = 0;
+      ICD_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<NC>, &cfg));
+      resident = std::max(1, n);
+    }
+    units = std::min(units, resident);
+  }
+  cfg.gridDim = dim3(std::min(tiles, units) * NC);
+  ICD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<NC>, ta, tb, tout, tres, p));
+  count_launch();
+  return ICD_OK;
+}
+
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) {
     set_error("gemm_tc: needs N %% %d == 0 and K %% %d == 0 (M=%d N=%d K=%d)", BN, BK, a.M, a.N, a.K);
     return ICD_E_ARG;
   }
-  ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   if (!a.tmap_out || (a.epi == EPI_BIAS_RESIDUAL && !a.tmap_res)) {
     set_error("gemm_tc: missing output / residual tensor map");
     return ICD_E_ARG;
@@ -330,12 +414,7 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.N = a.N;
   p.K = a.K;
   p.epi = a.epi;
-  const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
-  const int grid = std::min(tiles, kSMs);
-  gemm_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tout, tres, p);
-  count_launch();
-  ICD_CUDA(cudaGetLastError());
-  return ICD_OK;
+  return pair_mode() == 2 ? launch_nc<2>(ta, tb, tout, tres, p, st) : launch_nc<1>(ta, tb, tout, tres, p, st);
 }
 
 int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K) {
@@ -346,8 +425,9 @@ int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K) {
 int gemm_make_map_out(void* map128, const void* base, int64_t rows, int N) {
   return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)N, BM, kBoxCols, true);
 }
+// W box: the rows of the tile one CTA loads (all 256, or its half of the pair's tile)
 int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K) {
-  return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)K, BN, BK, true);
+  return make_tmap_bf16_2d(map128, base, (uint64_t)rows, (uint64_t)K, BN / pair_mode(), BK, true);
 }
 
 }  // namespace icd
