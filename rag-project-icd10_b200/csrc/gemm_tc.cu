@@ -46,7 +46,7 @@ template <int NC>
 struct Cfg {
   static constexpr int kBBytes = (BN / NC) * BK * 2;      // 32 / 16 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;   // 48 / 32 KiB
-  static constexpr int kStages = NC == 1 ? 4 : 6;         // 192 KiB of stages either way
+  static constexpr int kStages = NC == 1 ? 3 : 5;         // 144 / 160 KiB of stages
 };
 constexpr int kThreads = 320;
 constexpr int kEpiWarps = 8;
@@ -54,8 +54,13 @@ constexpr int kTmemCols = 512;
 constexpr int kBoxCols = 64;                    // staging box: 128 rows x 64 bf16 (128-byte rows)
 constexpr int kBoxBytes = BM * kBoxCols * 2;    // 16 KiB
 constexpr int kBoxesPerHalf = (BN / 2) / kBoxCols;  // 2
-constexpr int kSmemBytes = 4 * (kABytes + BN * BK * 2) + 2 * kBoxBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-static_assert(Cfg<1>::kStages * Cfg<1>::kStageBytes == Cfg<2>::kStages * Cfg<2>::kStageBytes, "same stage budget");
+constexpr int kStagingBoxes = 4;                // 2 column halves x 2 (double-buffered: a store drains while the next box fills)
+constexpr int kBiasBytes = 2 * 2 * (BN / 2) * 4;  // [half][tile parity][128] fp32
+template <int NC>
+constexpr int smem_bytes() {
+  return Cfg<NC>::kStages * Cfg<NC>::kStageBytes + kStagingBoxes * kBoxBytes + kBiasBytes + 256 /*barriers*/;
+}
+static_assert(smem_bytes<1>() <= 227 * 1024 && smem_bytes<2>() <= 227 * 1024, "shared memory budget");
 
 struct GemmParams {
   const float* bias;  // [N]
@@ -104,19 +109,19 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                const GemmParams p) {
-  extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment for the 128-byte swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic window starts 1024-aligned (128-byte swizzle atoms)
+  extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int kStages = Cfg<NC>::kStages, kStageBytes = Cfg<NC>::kStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* stage_c = smem + kStages * kStageBytes;  // [2 halves][128 x 64 bf16], 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + 2 * kBoxBytes);
+  unsigned char* stage_c = smem + kStages * kStageBytes;  // [2 halves][2 buffers][128 x 64 bf16], 1024-aligned
+  float* bias_s = reinterpret_cast<float*>(stage_c + kStagingBoxes * kBoxBytes);  // [2 halves][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + kStagingBoxes * kBoxBytes + kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [2] residual box landed (one per column half)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;  // [2 halves][2 buffers] residual box landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 4);
 
   // tile walk: a tile is BM * NC rows x BN columns; `unit` = CTA (NC = 1) or CTA pair (NC = 2)
   const uint32_t rank = NC == 2 ? ptx::cluster_ctarank() : 0u;  // 0 = leader of the pair (issues the MMAs)
@@ -138,7 +143,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
       ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), kEpiWarps * NC);  // the epilogue warps of every CTA of the tile
-      ptx::mbar_init(ptx::smem_u32(&res_bar[b]), 1);
+      ptx::mbar_init(ptx::smem_u32(&res_bar[2 * b]), 1);
+      ptx::mbar_init(ptx::smem_u32(&res_bar[2 * b + 1]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -230,32 +236,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const bool leader = (warp == 2 + 4 * half) && lane == 0;  // issues this group's TMA traffic
     const bool with_res = p.epi == EPI_BIAS_RESIDUAL;
-    unsigned char* box = stage_c + half * kBoxBytes;
-    const uint32_t box_u32 = ptx::smem_u32(box);
-    // this thread's row inside the box: 128 bytes, 16-byte chunk c lives at chunk (c ^ (row & 7))
-    unsigned char* my_row = box + row_in_tile * 128;
+    // two staging boxes per column half: while TMA drains box j (its reads queue behind the main loop's loads in
+    // the TMA unit -- ncu r01c showed the group waiting ~4 k cycles per box on a single buffer) box j+1 fills
+    unsigned char* box0 = stage_c + (size_t)half * 2 * kBoxBytes;
+    const uint32_t box0_u32 = ptx::smem_u32(box0);
+    // this thread's row inside a box: 128 bytes, 16-byte chunk c lives at chunk (c ^ (row & 7))
+    const int row_off = row_in_tile * 128;
     const int sw = row_in_tile & 7;
-    const uint32_t rbar = ptx::smem_u32(&res_bar[half]);
-    uint32_t res_phase = 0;
+    const uint32_t rbar0 = ptx::smem_u32(&res_bar[2 * half]);
+    uint32_t res_phase = 0;  // bit b = parity of this group's residual barrier b
+    float* my_bias = bias_s + half * 2 * (BN / 2);
     if (with_res && leader && unit < tiles) {
       const int m0 = (unit / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (unit % n_tiles) * BN;
-      ptx::mbar_expect_tx(rbar, kBoxBytes);
-      ptx::tma_load_2d(box_u32, &tmap_res, rbar, n0 + half * (BN / 2), m0);
+      ptx::mbar_expect_tx(rbar0, kBoxBytes);
+      ptx::tma_load_2d(box0_u32, &tmap_res, rbar0, n0 + half * (BN / 2), m0);
     }
     int it = 0;
+    int jb = 0;  // boxes this group has produced so far; buffer = jb & 1
     for (int tile = unit; tile < tiles; tile += units, ++it) {
       const int buf = it & 1;
       const int m0 = (tile / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (tile % n_tiles) * BN;
+      // this tile's 128 bias values of the column half: fetched before the accumulator wait, published through
+      // shared memory (a first-touch global load per 32-column chunk cost ~700 cycles each in r01c)
+      const float bv = p.bias[n0 + half * (BN / 2) + row_in_tile];
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
       ptx::tc_fence_after();
+      float* bias_t = my_bias + buf * (BN / 2);
+      bias_t[row_in_tile] = bv;  // last read two tiles ago; the group_sync below publishes it
 #pragma unroll 1
-      for (int bx = 0; bx < kBoxesPerHalf; ++bx) {
+      for (int bx = 0; bx < kBoxesPerHalf; ++bx, ++jb) {
         const int col0 = half * (BN / 2) + bx * kBoxCols;  // first column of this box within the tile
-        // the staging box is free once the leader has seen the previous store drain (it arrives here after that)
+        const int sb = jb & 1;
+        unsigned char* my_row = box0 + sb * kBoxBytes + row_off;
+        // buffer sb is free: the leader arrives here only after the store of box jb-2 has been read out
         group_sync(half);
         if (with_res) {
-          ptx::mbar_wait(rbar, res_phase);
-          res_phase ^= 1;
+          ptx::mbar_wait(rbar0 + 8 * sb, (res_phase >> sb) & 1);
+          res_phase ^= 1u << sb;
         }
 #pragma unroll
         for (int c32 = 0; c32 < kBoxCols / 32; ++c32) {
@@ -271,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[buf]), 0));  // the leader's barrier
             }
           }
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col0 + c32 * 32);
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_t + bx * kBoxCols + c32 * 32);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {  // 8 columns per 16-byte chunk
             float x[8];
@@ -311,9 +328,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::fence_proxy_async_smem();
         group_sync(half);
         if (leader) {
-          ptx::tma_store_2d(&tmap_out, box_u32, n0 + col0, m0);
+          ptx::tma_store_2d(&tmap_out, box0_u32 + sb * kBoxBytes, n0 + col0, m0);
           ptx::tma_store_commit();
-          ptx::tma_store_wait_read<0>();  // the box may be overwritten from here on
+          ptx::tma_store_wait_read<1>();  // the store of box jb-1 has drained: the other buffer is free
           if (with_res) {
             // prefetch the residual of the next box (same tile, or the first box of this CTA's next tile)
             int nm0 = m0, nc = n0 + col0 + kBoxCols;
@@ -325,8 +342,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               nc = (nt % n_tiles) * BN + half * (BN / 2);
             }
             if (more) {
-              ptx::mbar_expect_tx(rbar, kBoxBytes);
-              ptx::tma_load_2d(box_u32, &tmap_res, rbar, nc, nm0);
+              const uint32_t nb = (uint32_t)(sb ^ 1);
+              ptx::mbar_expect_tx(rbar0 + 8 * nb, kBoxBytes);
+              ptx::tma_load_2d(box0_u32 + nb * kBoxBytes, &tmap_res, rbar0 + 8 * nb, nc, nm0);
             }
           }
         }
@@ -362,6 +380,7 @@ static int pair_mode() {
 template <int NC>
 static int launch_nc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
                      const GemmParams& p, cudaStream_t st) {
+  constexpr int kSmemBytes = smem_bytes<NC>();
   ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((p.M + BM * NC - 1) / (BM * NC)) * (p.N / BN);
   cudaLaunchConfig_t cfg{};
