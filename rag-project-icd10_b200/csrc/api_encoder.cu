@@ -16,6 +16,7 @@
 //     output.dense.weight [H, I], .bias [H]
 //     output.LayerNorm.weight / .bias                            [H] [H]
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -35,6 +36,10 @@ struct LayerW {
   alignas(128) unsigned char m_2[128];
   // fp32 small parameters
   float *bqkv, *bo, *ln1g, *ln1b, *b1, *b2, *ln2g, *ln2b;
+  // deferred-LayerNorm mode (gemm_tc.cu header): wqkv / w1 hold W diag(gamma) of the LayerNorm in front of them,
+  // bqkv / b1 the matching b + W beta, cqkv / c1 the row sums of the folded bf16 weights (null: input is already
+  // normalised, layer 0's QKV), bo_r / b2_r the bias plus the beta of the LayerNorm the residual goes through
+  float *cqkv = nullptr, *c1 = nullptr, *bo_r = nullptr, *b2_r = nullptr;
 };
 
 }  // namespace icd
@@ -56,6 +61,10 @@ struct icd_encoder {
   alignas(128) unsigned char m_qkv[128];
   alignas(128) unsigned char m_t[128];        // GEMM output maps (box 128 x 64)
   alignas(128) unsigned char m_qkv_out[128];
+  // deferred LayerNorm: per-row partial (sum, sum sq) of the two pre-LayerNorm streams, [H/128][stats_stride] float2
+  bool fused_ln = true;
+  void *stats1 = nullptr, *stats2 = nullptr;
+  int stats_stride = 0;
   int32_t *ids = nullptr, *lens = nullptr;
   int ids_cap = 0, lens_cap = 0;
   void* out_stage = nullptr;
@@ -102,11 +111,21 @@ static int reserve_tokens(icd_encoder* e, int max_tokens) {
     if (*bufs[i]) cudaFree(*bufs[i]);
     *bufs[i] = nullptr;
   }
+  if (e->stats1) cudaFree(e->stats1);
+  if (e->stats2) cudaFree(e->stats2);
+  e->stats1 = e->stats2 = nullptr;
   e->max_tokens = 0;
   for (int i = 0; i < 6; ++i) {
     ICD_CUDA(cudaMalloc(bufs[i], (size_t)M * widths[i] * 2));
     ICD_CUDA(cudaMemset(*bufs[i], 0, (size_t)M * widths[i] * 2));
   }
+  // a CTA pair's tile is 256 rows: the statistics rows cover whole tiles
+  e->stats_stride = ((M + 255) / 256) * 256;
+  const size_t stats_bytes = (size_t)(H / 128) * e->stats_stride * 8;
+  ICD_CUDA(cudaMalloc(&e->stats1, stats_bytes));
+  ICD_CUDA(cudaMalloc(&e->stats2, stats_bytes));
+  ICD_CUDA(cudaMemset(e->stats1, 0, stats_bytes));
+  ICD_CUDA(cudaMemset(e->stats2, 0, stats_bytes));
   ICD_TRY(gemm_make_map_a(e->m_h, e->h, M, H));
   ICD_TRY(gemm_make_map_a(e->m_h1, e->h1, M, H));
   ICD_TRY(gemm_make_map_a(e->m_ctx, e->ctx, M, H));
@@ -116,6 +135,38 @@ static int reserve_tokens(icd_encoder* e, int max_tokens) {
   ICD_TRY(gemm_make_map_out(e->m_qkv_out, e->qkv, M, 3 * H));
   e->max_tokens = M;
   return ICD_OK;
+}
+
+// round-to-nearest-even fp32 -> bf16 -> fp32, the rounding f32_to_bf16_kernel applies on the device
+static float bf16_round_host(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Folds the LayerNorm (gamma, beta) in front of a linear layer y = LN(x) W^T + b into the layer:
+//   wf[n,k] = W[n,k] gamma[k];  bf[n] = b[n] + sum_k W[n,k] beta[k];  c[n] = sum_k bf16(wf[n,k])
+// so that y = rs (x wf^T) - rs mu c + bf with the row statistics applied in the GEMM epilogue.
+static void fold_layernorm(const float* W, const float* b, const float* gamma, const float* beta, int64_t n_out,
+                           int64_t n_in, std::vector<float>& wf, std::vector<float>& bf, std::vector<float>& c) {
+  wf.resize((size_t)n_out * n_in);
+  bf.resize((size_t)n_out);
+  c.resize((size_t)n_out);
+  for (int64_t n = 0; n < n_out; ++n) {
+    double bacc = b[n], cacc = 0.0;
+    const float* w = W + n * n_in;
+    float* o = wf.data() + n * n_in;
+    for (int64_t k = 0; k < n_in; ++k) {
+      o[k] = w[k] * gamma[k];
+      cacc += (double)bf16_round_host(o[k]);
+      bacc += (double)w[k] * (double)beta[k];
+    }
+    bf[n] = (float)bacc;
+    c[n] = (float)cacc;
+  }
 }
 
 }  // namespace icd
@@ -169,21 +220,72 @@ int icd_encoder_create(const float* weights, int64_t count, const icd_bert_cfg* 
   take((int64_t)cfg->type_vocab * H, false, (void**)&e->type);
   take(H, false, (void**)&e->eg);
   take(H, false, (void**)&e->eb);
+  // ICD_ENC_FUSED_LN=0 keeps the separate LayerNorm launches (A/B timing); the weights are prepared for one mode
+  {
+    const char* v = getenv("ICD_ENC_FUSED_LN");
+    e->fused_ln = !(v && *v && atoi(v) == 0);
+  }
+  const float *prev_g = nullptr, *prev_b = nullptr;  // host: the LayerNorm that closes the previous layer
+  std::vector<float> wf, bf, cf, sum;
+  auto upload_vec = [&](const std::vector<float>& v, float** dst) {
+    if (st != ICD_OK) return;
+    st = upload(e, v.data(), (int64_t)v.size(), false, (void**)dst, stage);
+  };
   for (int l = 0; l < cfg->layers && st == ICD_OK; ++l) {
     LayerW* L = new LayerW();
     e->layers.push_back(L);
-    take(3 * H * H, true, &L->wqkv);
-    take(3 * H, false, (void**)&L->bqkv);
+    const float* h_wqkv = w;
+    const float* h_bqkv = h_wqkv + 3 * H * H;
+    const float* h_wo = h_bqkv + 3 * H;
+    const float* h_bo = h_wo + H * H;
+    const float* h_g1 = h_bo + H;
+    const float* h_be1 = h_g1 + H;
+    const float* h_w1 = h_be1 + H;
+    const float* h_b1 = h_w1 + I * H;
+    const float* h_w2 = h_b1 + I;
+    const float* h_b2 = h_w2 + H * I;
+    const float* h_g2 = h_b2 + H;
+    const float* h_be2 = h_g2 + H;
+    if (e->fused_ln && prev_g) {
+      fold_layernorm(h_wqkv, h_bqkv, prev_g, prev_b, 3 * H, H, wf, bf, cf);
+      if (st == ICD_OK) st = upload(e, wf.data(), 3 * H * H, true, &L->wqkv, stage);
+      upload_vec(bf, &L->bqkv);
+      upload_vec(cf, &L->cqkv);
+      w += 3 * H * H + 3 * H;
+    } else {
+      take(3 * H * H, true, &L->wqkv);
+      take(3 * H, false, (void**)&L->bqkv);
+    }
     take(H * H, true, &L->wo);
     take(H, false, (void**)&L->bo);
     take(H, false, (void**)&L->ln1g);
     take(H, false, (void**)&L->ln1b);
-    take(I * H, true, &L->w1);
-    take(I, false, (void**)&L->b1);
+    if (e->fused_ln) {
+      fold_layernorm(h_w1, h_b1, h_g1, h_be1, I, H, wf, bf, cf);
+      if (st == ICD_OK) st = upload(e, wf.data(), I * H, true, &L->w1, stage);
+      upload_vec(bf, &L->b1);
+      upload_vec(cf, &L->c1);
+      w += I * H + I;
+    } else {
+      take(I * H, true, &L->w1);
+      take(I, false, (void**)&L->b1);
+    }
     take(H * I, true, &L->w2);
     take(H, false, (void**)&L->b2);
     take(H, false, (void**)&L->ln2g);
     take(H, false, (void**)&L->ln2b);
+    if (e->fused_ln) {
+      // the residual epilogues rebuild LN(x) = (x - mu) rs gamma + beta from the stream: beta rides in the bias
+      sum.assign(h_bo, h_bo + H);
+      if (prev_b)
+        for (int64_t i = 0; i < H; ++i) sum[i] += prev_b[i];
+      upload_vec(sum, &L->bo_r);
+      sum.assign(h_b2, h_b2 + H);
+      for (int64_t i = 0; i < H; ++i) sum[i] += h_be1[i];
+      upload_vec(sum, &L->b2_r);
+    }
+    prev_g = h_g2;
+    prev_b = h_be2;
     if (st != ICD_OK) break;
     st = gemm_make_map_b(L->m_qkv, L->wqkv, 3 * H, (int)H);
     if (st == ICD_OK) st = gemm_make_map_b(L->m_o, L->wo, H, (int)H);
@@ -203,7 +305,7 @@ int icd_encoder_destroy(icd_encoder* e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   for (auto* L : e->layers) delete L;
-  void* bufs[] = {e->h, e->h1, e->t, e->ctx, e->qkv, e->f, e->ids, e->lens, e->out_stage};
+  void* bufs[] = {e->h, e->h1, e->t, e->ctx, e->qkv, e->f, e->ids, e->lens, e->out_stage, e->stats1, e->stats2};
   for (void* p : bufs)
     if (p) cudaFree(p);
   delete e;
@@ -272,29 +374,65 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
 
   static const bool cuda_core_attention = getenv("ICD_ATTN_CUDA_CORE") != nullptr;  // A/B timing only
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
-  for (size_t l = 0; l < e->layers.size(); ++l) {
-    LayerW* L = e->layers[l];
-    GemmArgs g{};
-    // qkv = h Wqkv^T + b
-    g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->m_qkv_out, M, 3 * H, H, EPI_BIAS};
-    ICD_TRY(launch_gemm_tc(g, st));
-    if (cuda_core_attention)
-      ICD_TRY(launch_attention(e->qkv, d_lens, B, S, e->ctx, st));
-    else
-      ICD_TRY(launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, st));
-    // t = ctx Wo^T + bo + h ; h1 = LN(t)
-    g = GemmArgs{e->m_ctx, L->m_o, L->bo, e->m_h, e->m_t, M, H, H, EPI_BIAS_RESIDUAL};
-    ICD_TRY(launch_gemm_tc(g, st));
-    ICD_TRY(launch_layernorm(e->t, M, L->ln1g, L->ln1b, eps, e->h1, st));
-    // f = gelu(h1 W1^T + b1)
-    g = GemmArgs{e->m_h1, L->m_1, L->b1, nullptr, e->m_f, M, I, H, EPI_BIAS_GELU};
-    ICD_TRY(launch_gemm_tc(g, st));
-    // t = f W2^T + b2 + h1 ; h = LN(t)
-    g = GemmArgs{e->m_f, L->m_2, L->b2, e->m_h1, e->m_t, M, H, I, EPI_BIAS_RESIDUAL};
-    ICD_TRY(launch_gemm_tc(g, st));
-    ICD_TRY(launch_layernorm(e->t, M, L->ln2g, L->ln2b, eps, e->h, st));
+  auto attention = [&]() {
+    return cuda_core_attention ? launch_attention(e->qkv, d_lens, B, S, e->ctx, st)
+                               : launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, st);
+  };
+  const void* final_h = e->h;
+  if (e->fused_ln) {
+    // Deferred LayerNorm: e->h carries the layer input -- normalised for layer 0 (embed_ln), the un-normalised
+    // FFN-down output x2 = LN1(x1) + FFN(LN1(x1)) afterwards -- and e->t the un-normalised x1 = LN2(x2') + attn;
+    // stats2 / stats1 hold their row statistics.  No LayerNorm launch until the one that closes the last layer.
+    for (size_t l = 0; l < e->layers.size(); ++l) {
+      LayerW* L = e->layers[l];
+      const LayerW* P = l ? e->layers[l - 1] : nullptr;
+      const bool last = l + 1 == e->layers.size();
+      GemmArgs g{};
+      g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->m_qkv_out, M, 3 * H, H, EPI_BIAS};
+      if (P) g.vec2 = L->cqkv, g.stats_in = e->stats2;
+      g.stats_stride = e->stats_stride, g.stats_cols = H, g.eps = eps;
+      ICD_TRY(launch_gemm_tc(g, st));
+      ICD_TRY(attention());
+      // x1 = ctx Wo^T + bo + LN2'(x2')   (layer 0: + h)
+      g = GemmArgs{e->m_ctx, L->m_o, L->bo_r, e->m_h, e->m_t, M, H, H, EPI_BIAS_RESIDUAL};
+      if (P) g.vec2 = P->ln2g, g.stats_in = e->stats2;
+      g.stats_out = e->stats1, g.stats_stride = e->stats_stride, g.stats_cols = H, g.eps = eps;
+      ICD_TRY(launch_gemm_tc(g, st));
+      // f = gelu(LN1(x1) W1^T + b1)
+      g = GemmArgs{e->m_t, L->m_1, L->b1, nullptr, e->m_f, M, I, H, EPI_BIAS_GELU};
+      g.vec2 = L->c1, g.stats_in = e->stats1, g.stats_stride = e->stats_stride, g.stats_cols = H, g.eps = eps;
+      ICD_TRY(launch_gemm_tc(g, st));
+      // x2 = f W2^T + b2 + LN1(x1)
+      g = GemmArgs{e->m_f, L->m_2, L->b2_r, e->m_t, e->m_h, M, H, I, EPI_BIAS_RESIDUAL};
+      g.vec2 = L->ln1g, g.stats_in = e->stats1, g.stats_stride = e->stats_stride, g.stats_cols = H, g.eps = eps;
+      if (!last) g.stats_out = e->stats2;
+      ICD_TRY(launch_gemm_tc(g, st));
+    }
+    LayerW* L = e->layers.back();
+    ICD_TRY(launch_layernorm(e->h, M, L->ln2g, L->ln2b, eps, e->h1, st));
+    final_h = e->h1;
+  } else {
+    for (size_t l = 0; l < e->layers.size(); ++l) {
+      LayerW* L = e->layers[l];
+      GemmArgs g{};
+      // qkv = h Wqkv^T + b
+      g = GemmArgs{e->m_h, L->m_qkv, L->bqkv, nullptr, e->m_qkv_out, M, 3 * H, H, EPI_BIAS};
+      ICD_TRY(launch_gemm_tc(g, st));
+      ICD_TRY(attention());
+      // t = ctx Wo^T + bo + h ; h1 = LN(t)
+      g = GemmArgs{e->m_ctx, L->m_o, L->bo, e->m_h, e->m_t, M, H, H, EPI_BIAS_RESIDUAL};
+      ICD_TRY(launch_gemm_tc(g, st));
+      ICD_TRY(launch_layernorm(e->t, M, L->ln1g, L->ln1b, eps, e->h1, st));
+      // f = gelu(h1 W1^T + b1)
+      g = GemmArgs{e->m_h1, L->m_1, L->b1, nullptr, e->m_f, M, I, H, EPI_BIAS_GELU};
+      ICD_TRY(launch_gemm_tc(g, st));
+      // t = f W2^T + b2 + h1 ; h = LN(t)
+      g = GemmArgs{e->m_f, L->m_2, L->b2, e->m_h1, e->m_t, M, H, I, EPI_BIAS_RESIDUAL};
+      ICD_TRY(launch_gemm_tc(g, st));
+      ICD_TRY(launch_layernorm(e->t, M, L->ln2g, L->ln2b, eps, e->h, st));
+    }
   }
-  ICD_TRY(launch_pool_normalise(e->h, d_lens, B, S, d_out, out_flags, st));
+  ICD_TRY(launch_pool_normalise(final_h, d_lens, B, S, d_out, out_flags, st));
   e->last_M = M;
   if (host_out) {
     ICD_CUDA(cudaMemcpyAsync(out, d_out, (size_t)B * H * (out_dtype == ICD_F32 ? 4 : 2), cudaMemcpyDeviceToHost, st));
@@ -310,7 +448,7 @@ int icd_encoder_read_hidden(icd_encoder* e, int layer_unused, float* out, int64_
   ICD_CUDA(cudaSetDevice(e->device));
   float* tmp = nullptr;
   ICD_CUDA(cudaMalloc((void**)&tmp, (size_t)count * 4));
-  int st = launch_bf16_to_f32(e->h, tmp, count, 0);
+  int st = launch_bf16_to_f32(e->fused_ln ? e->h1 : e->h, tmp, count, 0);
   if (st == ICD_OK) {
     cudaError_t err = cudaMemcpy(out, tmp, (size_t)count * 4, cudaMemcpyDefault);
     if (err != cudaSuccess) {

@@ -16,6 +16,13 @@ struct GemmArgs {
   const void* tmap_out;  // CUtensorMap of out [rows,N] bf16 (box 128 x 64); rows is a multiple of 128 >= M
   int M, N, K;
   int epi;
+  // deferred LayerNorm (gemm_tc.cu header); all optional
+  const float* vec2 = nullptr;      // [N] fp32: c = row sums of the gamma-folded W (A is a pre-LN stream), or gamma (residual is one)
+  const void* stats_in = nullptr;   // [stats_cols / 128][stats_stride] float2 partial (sum, sum sq) per row of that stream
+  void* stats_out = nullptr;        // [N / 128][stats_stride] float2 partials of this GEMM's output rows
+  int stats_stride = 0;             // rows per slot, a multiple of 256 >= M
+  int stats_cols = 0;               // row length the incoming statistics cover (768)
+  float eps = 0.0f;
 };
 int gemm_tile_n();
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st);

@@ -21,6 +21,15 @@
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..9 epilogue (lane quarter = warp % 4, column half = (warp - 2) / 4).
 //
+// Deferred LayerNorm.  The two LayerNorm launches per layer were 9 % of the encoder (HBM-bound, r01c launch
+// list); they are folded into the GEMMs on either side instead.  A GEMM whose output feeds a LayerNorm
+// (O projection, FFN down) also emits per-row partial (sum, sum of squares) of its 128 output columns per
+// column half -- [N/128][rows] float2, no atomics, deterministic.  A GEMM that READS a LayerNorm output
+// takes the un-normalised stream x as A with W' = W diag(gamma) pre-folded on the host and applies
+//   y = rs * (x W'^T) - rs * mu * c + b',   c[n] = sum_k W'[n,k],  b' = b + W beta
+// per row in its epilogue (the identity CUTLASS's gemm+layernorm fusion uses); a residual epilogue that needs
+// LN(x) itself rebuilds it from the TMA-loaded box: (x - mu) rs gamma[n] (+ beta folded into the bias).
+//
 // Roofline: bf16 tensor pipe; 2*M*N*K flops per launch.
 #include <stdlib.h>
 #include <string.h>
@@ -55,7 +64,7 @@ constexpr int kBoxCols = 64;                    // staging box: 128 rows x 64 bf
 constexpr int kBoxBytes = BM * kBoxCols * 2;    // 16 KiB
 constexpr int kBoxesPerHalf = (BN / 2) / kBoxCols;  // 2
 constexpr int kStagingBoxes = 4;                // 2 column halves x 2 (double-buffered: a store drains while the next box fills)
-constexpr int kBiasBytes = 2 * 2 * (BN / 2) * 4;  // [half][tile parity][128] fp32
+constexpr int kBiasBytes = 2 * 2 * (BN / 2) * 4;  // [half][bias | second column vector][128] fp32
 template <int NC>
 constexpr int smem_bytes() {
   return Cfg<NC>::kStages * Cfg<NC>::kStageBytes + kStagingBoxes * kBoxBytes + kBiasBytes + 256 /*barriers*/;
@@ -64,6 +73,11 @@ static_assert(smem_bytes<1>() <= 227 * 1024 && smem_bytes<2>() <= 227 * 1024, "s
 
 struct GemmParams {
   const float* bias;  // [N]
+  const float* vec2;  // [N] c (A is a pre-LayerNorm stream) or gamma (residual is one); null otherwise
+  const float2* stats_in;  // [slots_in][stats_stride] partial (sum, sum sq) of the rows of A / of the residual, or null
+  float2* stats_out;       // [N / 128][stats_stride] partials of this GEMM's output rows, or null
+  int stats_stride, slots_in;
+  float inv_h, eps;   // 1 / (row length the statistics cover), LayerNorm eps
   int M, N, K;
   int epi;            // GemmEpilogue
 };
@@ -245,7 +259,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int sw = row_in_tile & 7;
     const uint32_t rbar0 = ptx::smem_u32(&res_bar[2 * half]);
     uint32_t res_phase = 0;  // bit b = parity of this group's residual barrier b
-    float* my_bias = bias_s + half * 2 * (BN / 2);
+    float* bias_t = bias_s + half * 2 * (BN / 2);  // this group's [bias | vec2], one tile at a time
+    float* vec2_t = bias_t + BN / 2;
+    const bool ln_in = p.stats_in != nullptr && !with_res;   // A rows are un-normalised: scale/shift per row here
+    const bool want_stats = p.stats_out != nullptr;
     if (with_res && leader && unit < tiles) {
       const int m0 = (unit / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (unit % n_tiles) * BN;
       ptx::mbar_expect_tx(rbar0, kBoxBytes);
@@ -259,10 +276,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // this tile's 128 bias values of the column half: fetched before the accumulator wait, published through
       // shared memory (a first-touch global load per 32-column chunk cost ~700 cycles each in r01c)
       const float bv = p.bias[n0 + half * (BN / 2) + row_in_tile];
+      const float v2 = p.vec2 ? p.vec2[n0 + half * (BN / 2) + row_in_tile] : 1.0f;
+      // LayerNorm statistics of this thread's row (of A, or of the residual): rs = 1/sigma, nmr = -mu/sigma
+      float rs = 1.0f, nmr = 0.0f;
+      if (p.stats_in) {
+        float s = 0.0f, ss = 0.0f;
+        for (int j = 0; j < p.slots_in; ++j) {
+          const float2 v = p.stats_in[(size_t)j * p.stats_stride + m0 + row_in_tile];
+          s += v.x;
+          ss += v.y;
+        }
+        const float mu = s * p.inv_h;
+        rs = rsqrtf(fmaxf(fmaf(-mu, mu, ss * p.inv_h), 0.0f) + p.eps);
+        nmr = -mu * rs;
+      }
+      float row_s = 0.0f, row_ss = 0.0f;  // partial statistics of this row's 128 output columns
       ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
       ptx::tc_fence_after();
-      float* bias_t = my_bias + buf * (BN / 2);
-      bias_t[row_in_tile] = bv;  // last read two tiles ago; the group_sync below publishes it
+      // every thread of the group left the previous tile's last box through a group_sync, so the vectors are free;
+      // the group_sync below publishes them
+      bias_t[row_in_tile] = bv;
+      vec2_t[row_in_tile] = v2;
 #pragma unroll 1
       for (int bx = 0; bx < kBoxesPerHalf; ++bx, ++jb) {
         const int col0 = half * (BN / 2) + bx * kBoxCols;  // first column of this box within the tile
@@ -289,32 +323,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           const float4* bias4 = reinterpret_cast<const float4*>(bias_t + bx * kBoxCols + c32 * 32);
+          const float4* vec4 = reinterpret_cast<const float4*>(vec2_t + bx * kBoxCols + c32 * 32);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {  // 8 columns per 16-byte chunk
-            float x[8];
-            const float4 b0 = bias4[2 * v], b1 = bias4[2 * v + 1];
-            x[0] = __uint_as_float(r[8 * v + 0]) + b0.x;
-            x[1] = __uint_as_float(r[8 * v + 1]) + b0.y;
-            x[2] = __uint_as_float(r[8 * v + 2]) + b0.z;
-            x[3] = __uint_as_float(r[8 * v + 3]) + b0.w;
-            x[4] = __uint_as_float(r[8 * v + 4]) + b1.x;
-            x[5] = __uint_as_float(r[8 * v + 5]) + b1.y;
-            x[6] = __uint_as_float(r[8 * v + 6]) + b1.z;
-            x[7] = __uint_as_float(r[8 * v + 7]) + b1.w;
+            float x[8], g[8];
+            {
+              const float4 b0 = bias4[2 * v], b1 = bias4[2 * v + 1];
+              x[0] = b0.x, x[1] = b0.y, x[2] = b0.z, x[3] = b0.w;
+              x[4] = b1.x, x[5] = b1.y, x[6] = b1.z, x[7] = b1.w;
+            }
+            if (ln_in || with_res) {
+              const float4 g0 = vec4[2 * v], g1 = vec4[2 * v + 1];
+              g[0] = g0.x, g[1] = g0.y, g[2] = g0.z, g[3] = g0.w;
+              g[4] = g1.x, g[5] = g1.y, g[6] = g1.z, g[7] = g1.w;
+            }
+            if (ln_in) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = fmaf(__uint_as_float(r[8 * v + e]), rs, fmaf(nmr, g[e], x[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] += __uint_as_float(r[8 * v + e]);
+            }
             uint4* slot = reinterpret_cast<uint4*>(my_row + (((c32 * 4 + v) ^ sw) << 4));
             if (p.epi == EPI_BIAS_GELU) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
             } else if (with_res) {
+              // residual = LayerNorm of the loaded stream when statistics came along (rs, nmr, gamma; beta sits in the
+              // bias), the stream itself otherwise (rs = 1, nmr = 0, gamma = 1)
               const uint4 rr = *slot;
-              x[0] += bf16lo_to_f32(rr.x);
-              x[1] += bf16hi_to_f32(rr.x);
-              x[2] += bf16lo_to_f32(rr.y);
-              x[3] += bf16hi_to_f32(rr.y);
-              x[4] += bf16lo_to_f32(rr.z);
-              x[5] += bf16hi_to_f32(rr.z);
-              x[6] += bf16lo_to_f32(rr.w);
-              x[7] += bf16hi_to_f32(rr.w);
+              x[0] = fmaf(fmaf(bf16lo_to_f32(rr.x), rs, nmr), g[0], x[0]);
+              x[1] = fmaf(fmaf(bf16hi_to_f32(rr.x), rs, nmr), g[1], x[1]);
+              x[2] = fmaf(fmaf(bf16lo_to_f32(rr.y), rs, nmr), g[2], x[2]);
+              x[3] = fmaf(fmaf(bf16hi_to_f32(rr.y), rs, nmr), g[3], x[3]);
+              x[4] = fmaf(fmaf(bf16lo_to_f32(rr.z), rs, nmr), g[4], x[4]);
+              x[5] = fmaf(fmaf(bf16hi_to_f32(rr.z), rs, nmr), g[5], x[5]);
+              x[6] = fmaf(fmaf(bf16lo_to_f32(rr.w), rs, nmr), g[6], x[6]);
+              x[7] = fmaf(fmaf(bf16hi_to_f32(rr.w), rs, nmr), g[7], x[7]);
+            }
+            if (want_stats) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                row_s += x[e];
+                row_ss = fmaf(x[e], x[e], row_ss);
+              }
             }
             uint4 o;
             o.x = pack_bf16(x[0], x[1]);
@@ -349,6 +401,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+      if (want_stats)
+        p.stats_out[(size_t)((n0 >> 7) + half) * p.stats_stride + m0 + row_in_tile] = make_float2(row_s, row_ss);
     }
     if (leader) ptx::tma_store_wait_all();  // global writes complete before the kernel ends
   }
@@ -418,6 +472,11 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     set_error("gemm_tc: needs N %% %d == 0 and K %% %d == 0 (M=%d N=%d K=%d)", BN, BK, a.M, a.N, a.K);
     return ICD_E_ARG;
   }
+  if ((a.stats_in || a.stats_out) &&
+      (a.stats_stride < ((a.M + 2 * BM - 1) / (2 * BM)) * 2 * BM || (a.stats_in && (a.stats_cols <= 0 || a.stats_cols % 128 != 0 || !a.vec2)))) {
+    set_error("gemm_tc: LayerNorm statistics need a row stride covering whole tiles, the column vector, and a row length %% 128 == 0");
+    return ICD_E_ARG;
+  }
   if (!a.tmap_out || (a.epi == EPI_BIAS_RESIDUAL && !a.tmap_res)) {
     set_error("gemm_tc: missing output / residual tensor map");
     return ICD_E_ARG;
@@ -429,6 +488,13 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   memcpy(&tres, a.tmap_res ? a.tmap_res : a.tmap_out, sizeof(tres));
   GemmParams p{};
   p.bias = a.bias;
+  p.vec2 = a.vec2;
+  p.stats_in = reinterpret_cast<const float2*>(a.stats_in);
+  p.stats_out = reinterpret_cast<float2*>(a.stats_out);
+  p.stats_stride = a.stats_stride;
+  p.slots_in = a.stats_in ? a.stats_cols / 128 : 0;
+  p.inv_h = a.stats_cols > 0 ? 1.0f / (float)a.stats_cols : 0.0f;
+  p.eps = a.eps;
   p.M = a.M;
   p.N = a.N;
   p.K = a.K;

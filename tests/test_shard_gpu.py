@@ -14,7 +14,7 @@ def test_sharded_search_equals_single_table():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
-    world = 2 if n < 4 else 4
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "shard_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
