@@ -1,0 +1,25 @@
+"""Times the encoder alone (B=4096, S=64, 12 layers, synthetic): ENC_REPS timed batches after 3 warm-ups."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+E = importlib.import_module("rag-project-icd10_b200.engine.encoder")
+B, S = int(os.environ.get("ENC_B", 4096)), int(os.environ.get("ENC_S", 64))
+reps = int(os.environ.get("ENC_REPS", 20))
+eng = E.synthetic_engine(device=0, max_tokens=B * S)
+ids = torch.randint(1000, 21128, (B, S), device="cuda", dtype=torch.int32)
+lens = torch.full((B,), S, dtype=torch.int32, device="cuda")
+out = torch.empty((B, 768), dtype=torch.float32, device="cuda")
+for _ in range(3):
+    eng.forward_ids(ids, lens, out=out)
+torch.cuda.synchronize()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(reps):
+    eng.forward_ids(ids, lens, out=out)
+t1.record()
+torch.cuda.synchronize()
+ms = t0.elapsed_time(t1) / reps
+flops = B * S * 12 * (2 * (4 * 768 * 768 + 2 * 768 * 3072) + 4 * S * 768)
+print({"fused_ln": os.environ.get("ICD_ENC_FUSED_LN", "1"), "pair": os.environ.get("ICD_GEMM_PAIR", "1"), "B": B, "S": S,
+       "ms_per_batch": round(ms, 3), "sentences_per_s": round(B / ms * 1e3), "tflops": round(flops / ms / 1e9, 1),
+       "mean_norm": float(out.norm(dim=1).mean())})

@@ -64,6 +64,7 @@ constexpr int kBoxCols = 64;                    // staging box: 128 rows x 64 bf
 constexpr int kBoxBytes = BM * kBoxCols * 2;    // 16 KiB
 constexpr int kBoxesPerHalf = (BN / 2) / kBoxCols;  // 2
 constexpr int kStagingBoxes = 4;                // 2 column halves x 2 (double-buffered: a store drains while the next box fills)
+constexpr int kStatSlots = 6;                   // LayerNorm row length 768 = 6 column halves of 128
 constexpr int kBiasBytes = 2 * 2 * (BN / 2) * 4;  // [half][bias | second column vector][128] fp32
 template <int NC>
 constexpr int smem_bytes() {
@@ -76,7 +77,7 @@ struct GemmParams {
   const float* vec2;  // [N] c (A is a pre-LayerNorm stream) or gamma (residual is one); null otherwise
   const float2* stats_in;  // [slots_in][stats_stride] partial (sum, sum sq) of the rows of A / of the residual, or null
   float2* stats_out;       // [N / 128][stats_stride] partials of this GEMM's output rows, or null
-  int stats_stride, slots_in;
+  int stats_stride;
   float inv_h, eps;   // 1 / (row length the statistics cover), LayerNorm eps
   int M, N, K;
   int epi;            // GemmEpilogue
@@ -88,29 +89,26 @@ __device__ __forceinline__ void group_sync(int half) {
 }
 
 // HF "gelu" = x * Phi(x) with Phi(x) = 0.5 * (1 + erf(x / sqrt(2))).  The epilogue of the FFN-up GEMM
-// evaluates 32 K of these per 128 x 256 tile while the next tile's MMAs run, so it has to fit ~20 issue
-// slots per element: Phi is evaluated as a logistic of an odd quintic fitted to the erf form,
-//   Phi(x) ~= 1 / (1 + exp(-2 (c x + a x^3 + b x^5))),   max |x Phi(x) - gelu_erf(x)| = 2.6e-5 over all x
-// (c, a, b from a minimax fit, tests/test_encoder_gpu.py checks the formula against erf): 7 FP32
-// instructions + ex2.approx + rcp.approx, no branches.  x^2 is clamped so the quintic stays monotone.
-__device__ __forceinline__ float ex2_approx(float x) {
+// evaluates 32 K of these per 128 x 256 tile while the next tile's MMAs run (K = 768: the MMAs of a tile take
+// about as long as its epilogue), so every instruction counts.  Phi is evaluated as a logistic of an odd quintic
+// fitted to the erf form, written through tanh so that it costs ONE MUFU op:
+//   Phi(x) ~= 1 / (1 + exp(-2 u)) = 0.5 (1 + tanh(u)),  u = c x + a x^3 + b x^5
+//   gelu(x) ~= hx + hx tanh(u),  hx = x / 2
+// (c, a, b from a minimax fit: max |x Phi(x) - gelu_erf(x)| = 2.6e-5 with exact tanh; tanh.approx.f32 adds at most
+// 2^-11 |hx|, below the bf16 rounding of the stored value; tests/test_encoder_gpu.py checks the formula against
+// erf).  x^2 is clamped so the quintic stays monotone.  8 FP32 instructions, no branches.
+__device__ __forceinline__ float tanh_approx(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  constexpr float kS = -2.0f * 1.4426950408889634f;  // exp(-2 u) = exp2(kS * u)
-  constexpr float kC = kS * 7.97507884e-01f, kA = kS * 3.70056460e-02f, kB = kS * -3.51516788e-04f;
+  constexpr float kC = 7.97507884e-01f, kA = 3.70056460e-02f, kB = -3.51516788e-04f;
   const float t = fminf(x * x, 36.0f);
   float p = fmaf(kB, t, kA);
   p = fmaf(p, t, kC);
-  const float e = ex2_approx(p * x);
-  return x * rcp_approx(1.0f + e);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(p * x), hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -118,7 +116,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int NC>
+// EPI / LNIN / STATS are compile-time so that the 32 columns of an accumulator chunk form one straight-line block
+// (r01d: with run-time epilogue switches every 8-column group was fenced by uniform branches, and the shared-memory
+// loads of the column vectors stalled their first use -- 2 epilogue warps per scheduler cannot hide that).
+//   LNIN: A is an un-normalised stream, apply its row statistics (QKV / FFN-up in deferred-LayerNorm mode)
+//   STATS: emit the row statistics of the output (residual epilogues in deferred-LayerNorm mode)
+template <int NC, int EPI, bool LNIN, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -149,7 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
     ptx::prefetch_tmap(&tmap_out);
-    if (p.epi == EPI_BIAS_RESIDUAL) ptx::prefetch_tmap(&tmap_res);
+    if (EPI == EPI_BIAS_RESIDUAL) ptx::prefetch_tmap(&tmap_res);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
@@ -249,7 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row_in_tile = 32 * quarter + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const bool leader = (warp == 2 + 4 * half) && lane == 0;  // issues this group's TMA traffic
-    const bool with_res = p.epi == EPI_BIAS_RESIDUAL;
+    constexpr bool with_res = EPI == EPI_BIAS_RESIDUAL;
     // two staging boxes per column half: while TMA drains box j (its reads queue behind the main loop's loads in
     // the TMA unit -- ncu r01c showed the group waiting ~4 k cycles per box on a single buffer) box j+1 fills
     unsigned char* box0 = stage_c + (size_t)half * 2 * kBoxBytes;
@@ -261,8 +264,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t res_phase = 0;  // bit b = parity of this group's residual barrier b
     float* bias_t = bias_s + half * 2 * (BN / 2);  // this group's [bias | vec2], one tile at a time
     float* vec2_t = bias_t + BN / 2;
-    const bool ln_in = p.stats_in != nullptr && !with_res;   // A rows are un-normalised: scale/shift per row here
-    const bool want_stats = p.stats_out != nullptr;
+    constexpr bool ln_in = LNIN;  // A rows are un-normalised: scale/shift per row here
+    constexpr bool want_stats = STATS;
+    const bool have_stats = (LNIN || with_res) && p.stats_in != nullptr;  // a plain residual carries none
     if (with_res && leader && unit < tiles) {
       const int m0 = (unit / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (unit % n_tiles) * BN;
       ptx::mbar_expect_tx(rbar0, kBoxBytes);
@@ -270,21 +274,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     int it = 0;
     int jb = 0;  // boxes this group has produced so far; buffer = jb & 1
+    // Per-tile operands of this thread, requested one tile ahead so their L2 latency hides behind the previous
+    // tile's epilogue (r01d: six dependent statistics loads per tile in front of the accumulator wait were 12 % of
+    // the FFN-up GEMM's stall samples): the bias / second-vector element this thread publishes through shared
+    // memory and the LayerNorm partials of its row.
+    float nx_bias = 0.0f, nx_vec2 = 1.0f;
+    float2 nx_stat[kStatSlots];
+    auto request = [&](int t) {
+      const int tm0 = (t / n_tiles) * (BM * NC) + (int)rank * BM, tn0 = (t % n_tiles) * BN;
+      nx_bias = p.bias[tn0 + half * (BN / 2) + row_in_tile];
+      if ((LNIN || with_res) && p.vec2) nx_vec2 = p.vec2[tn0 + half * (BN / 2) + row_in_tile];
+      if (have_stats) {
+#pragma unroll
+        for (int j = 0; j < kStatSlots; ++j) nx_stat[j] = p.stats_in[(size_t)j * p.stats_stride + tm0 + row_in_tile];
+      }
+    };
+    if (unit < tiles) request(unit);
     for (int tile = unit; tile < tiles; tile += units, ++it) {
       const int buf = it & 1;
       const int m0 = (tile / n_tiles) * (BM * NC) + (int)rank * BM, n0 = (tile % n_tiles) * BN;
-      // this tile's 128 bias values of the column half: fetched before the accumulator wait, published through
-      // shared memory (a first-touch global load per 32-column chunk cost ~700 cycles each in r01c)
-      const float bv = p.bias[n0 + half * (BN / 2) + row_in_tile];
-      const float v2 = p.vec2 ? p.vec2[n0 + half * (BN / 2) + row_in_tile] : 1.0f;
+      const float bv = nx_bias, v2 = nx_vec2;
       // LayerNorm statistics of this thread's row (of A, or of the residual): rs = 1/sigma, nmr = -mu/sigma
       float rs = 1.0f, nmr = 0.0f;
-      if (p.stats_in) {
+      if (have_stats) {
         float s = 0.0f, ss = 0.0f;
-        for (int j = 0; j < p.slots_in; ++j) {
-          const float2 v = p.stats_in[(size_t)j * p.stats_stride + m0 + row_in_tile];
-          s += v.x;
-          ss += v.y;
+#pragma unroll
+        for (int j = 0; j < kStatSlots; ++j) {
+          s += nx_stat[j].x;
+          ss += nx_stat[j].y;
         }
         const float mu = s * p.inv_h;
         rs = rsqrtf(fmaxf(fmaf(-mu, mu, ss * p.inv_h), 0.0f) + p.eps);
@@ -297,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // the group_sync below publishes them
       bias_t[row_in_tile] = bv;
       vec2_t[row_in_tile] = v2;
+      if (tile + units < tiles) request(tile + units);
 #pragma unroll 1
       for (int bx = 0; bx < kBoxesPerHalf; ++bx, ++jb) {
         const int col0 = half * (BN / 2) + bx * kBoxCols;  // first column of this box within the tile
@@ -345,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int e = 0; e < 8; ++e) x[e] += __uint_as_float(r[8 * v + e]);
             }
             uint4* slot = reinterpret_cast<uint4*>(my_row + (((c32 * 4 + v) ^ sw) << 4));
-            if (p.epi == EPI_BIAS_GELU) {
+            if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
             } else if (with_res) {
@@ -401,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-      if (want_stats)
+      if (want_stats && p.stats_out)
         p.stats_out[(size_t)((n0 >> 7) + half) * p.stats_stride + m0 + row_in_tile] = make_float2(row_s, row_ss);
     }
     if (leader) ptx::tma_store_wait_all();  // global writes complete before the kernel ends
@@ -431,11 +449,12 @@ static int pair_mode() {
   return mode;
 }
 
-template <int NC>
-static int launch_nc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
-                     const GemmParams& p, cudaStream_t st) {
+template <int NC, int EPI, bool LNIN, bool STATS>
+static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
+                          const GemmParams& p, cudaStream_t st) {
   constexpr int kSmemBytes = smem_bytes<NC>();
-  ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  auto kernel = gemm_tc_kernel<NC, EPI, LNIN, STATS>;
+  ICD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((p.M + BM * NC - 1) / (BM * NC)) * (p.N / BN);
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kThreads);
@@ -456,15 +475,35 @@ static int launch_nc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtenso
     if (resident == 0) {
       cfg.gridDim = dim3(kSMs);
       int n = 0;
-      ICD_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<NC>, &cfg));
+      ICD_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
       resident = std::max(1, n);
     }
     units = std::min(units, resident);
   }
   cfg.gridDim = dim3(std::min(tiles, units) * NC);
-  ICD_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<NC>, ta, tb, tout, tres, p));
+  ICD_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tout, tres, p));
   count_launch();
   return ICD_OK;
+}
+
+template <int NC>
+static int launch_nc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
+                     const GemmParams& p, cudaStream_t st) {
+  const bool lnin = p.stats_in != nullptr && p.epi != EPI_BIAS_RESIDUAL;
+  const bool stats = p.stats_out != nullptr;
+  switch (p.epi) {
+    case EPI_BIAS:
+      return lnin ? launch_variant<NC, EPI_BIAS, true, false>(ta, tb, tout, tres, p, st)
+                  : launch_variant<NC, EPI_BIAS, false, false>(ta, tb, tout, tres, p, st);
+    case EPI_BIAS_GELU:
+      return lnin ? launch_variant<NC, EPI_BIAS_GELU, true, false>(ta, tb, tout, tres, p, st)
+                  : launch_variant<NC, EPI_BIAS_GELU, false, false>(ta, tb, tout, tres, p, st);
+    case EPI_BIAS_RESIDUAL:
+      return stats ? launch_variant<NC, EPI_BIAS_RESIDUAL, false, true>(ta, tb, tout, tres, p, st)
+                   : launch_variant<NC, EPI_BIAS_RESIDUAL, false, false>(ta, tb, tout, tres, p, st);
+  }
+  set_error("gemm_tc: unknown epilogue %d", p.epi);
+  return ICD_E_ARG;
 }
 
 int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
@@ -473,8 +512,8 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
     return ICD_E_ARG;
   }
   if ((a.stats_in || a.stats_out) &&
-      (a.stats_stride < ((a.M + 2 * BM - 1) / (2 * BM)) * 2 * BM || (a.stats_in && (a.stats_cols <= 0 || a.stats_cols % 128 != 0 || !a.vec2)))) {
-    set_error("gemm_tc: LayerNorm statistics need a row stride covering whole tiles, the column vector, and a row length %% 128 == 0");
+      (a.stats_stride < ((a.M + 2 * BM - 1) / (2 * BM)) * 2 * BM || (a.stats_in && (a.stats_cols != 128 * kStatSlots || !a.vec2)))) {
+    set_error("gemm_tc: LayerNorm statistics need a row stride covering whole tiles, the column vector, and a row length of 768");
     return ICD_E_ARG;
   }
   if (!a.tmap_out || (a.epi == EPI_BIAS_RESIDUAL && !a.tmap_res)) {
@@ -492,7 +531,6 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.stats_in = reinterpret_cast<const float2*>(a.stats_in);
   p.stats_out = reinterpret_cast<float2*>(a.stats_out);
   p.stats_stride = a.stats_stride;
-  p.slots_in = a.stats_in ? a.stats_cols / 128 : 0;
   p.inv_h = a.stats_cols > 0 ? 1.0f / (float)a.stats_cols : 0.0f;
   p.eps = a.eps;
   p.M = a.M;
