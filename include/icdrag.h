@@ -113,7 +113,11 @@ int icd_index_search(icd_index* idx, const void* q, int q_dtype, int B, int k, i
 /* kernels launched / microseconds of device time of the last search on this handle, split by
  * stage: [0] scan, [1] merge, [2] rescore+finalise.  For bench.py's roofline line. */
 int icd_index_last_timing(const icd_index* idx, float* us3, int* launches);
-int icd_index_set_timing(icd_index* idx, int enabled);
+int icd_index_set_timing(icd_index* idx, int enabled);   /* also restarts the call count below */
+/* the same three stage times averaged over the searches issued since icd_index_set_timing(idx, 1)
+ * (the most recent 64 of them); *calls = how many were averaged.  Synchronises with the last one only,
+ * so a timed region of back-to-back searches is measured without host syncs in between. */
+int icd_index_mean_timing(const icd_index* idx, float* us3, int* calls);
 
 /* ---------------------------------------------------------------- row-sharded scan ---------
  * New work (the reference is single-process): rank r holds rows [row_offset, row_offset+n_r);

@@ -376,7 +376,7 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
   auto attention = [&]() {
     return cuda_core_attention ? launch_attention(e->qkv, d_lens, B, S, e->ctx, st)
-                               : launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, st);
+                               : launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st);
   };
   const void* final_h = e->h;
   if (e->fused_ln) {

@@ -114,6 +114,7 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
   ICD_TRY(x->cand_score.reserve((size_t)B * kc * 4));
   ICD_TRY(x->cand_id.reserve((size_t)B * kc * 8));
 
+  if (x->timing) x->ev = x->ev_ring[x->timed_calls++ % icd_index::kTimingRing];
   cudaEvent_t* ev = x->ev;
   if (x->timing) cudaEventRecord(ev[0], st);
   const int64_t l0 = g_launches.load();
@@ -323,7 +324,8 @@ int icd_index_create(int dim, int device, int64_t capacity_rows, int flags, icd_
     delete x;
     return st;
   }
-  for (int i = 0; i < 4; ++i) cudaEventCreate(&x->ev[i]);
+  for (int r = 0; r < icd_index::kTimingRing; ++r)
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&x->ev_ring[r][i]);
   *out = x;
   return ICD_OK;
 }
@@ -346,7 +348,8 @@ int icd_index_destroy(icd_index* x) {
   x->out_stage.release();
   x->in_stage.release();
   x->gbound.release();
-  for (int i = 0; i < 4; ++i) cudaEventDestroy(x->ev[i]);
+  for (int r = 0; r < icd_index::kTimingRing; ++r)
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(x->ev_ring[r][i]);
   delete x;
   return ICD_OK;
 }
@@ -503,6 +506,29 @@ int icd_index_search(icd_index* x, const void* q, int q_dtype, int B, int k, int
 int icd_index_set_timing(icd_index* x, int enabled) {
   ICD_CHECK_ARG(x != nullptr, "index is null");
   x->timing = enabled != 0;
+  x->timed_calls = 0;
+  x->timing_pending = false;
+  return ICD_OK;
+}
+
+int icd_index_mean_timing(const icd_index* x, float* us3, int* calls) {
+  ICD_CHECK_ARG(x != nullptr && us3 != nullptr, "null argument");
+  us3[0] = us3[1] = us3[2] = 0.f;
+  const int n = (int)std::min<int64_t>(x->timed_calls, icd_index::kTimingRing);
+  if (calls) *calls = n;
+  if (n == 0 || !x->timing_pending) return ICD_OK;
+  DeviceGuard g(x->device);
+  ICD_CUDA(cudaEventSynchronize(x->ev[3]));
+  double acc[3] = {0, 0, 0};
+  for (int c = 0; c < n; ++c) {
+    const cudaEvent_t* q = x->ev_ring[(x->timed_calls - 1 - c) % icd_index::kTimingRing];
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      ICD_CUDA(cudaEventElapsedTime(&ms, q[i], q[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < 3; ++i) us3[i] = (float)(acc[i] * 1000.0 / n);
   return ICD_OK;
 }
 

@@ -12,14 +12,22 @@
 //            un-normalised P goes back to TMEM as packed bf16 (64 columns) with tcgen05.st
 //   MMA 2    O = P V             tcgen05 TS: A = P from TMEM, B = V read MN-major from the same
 //            swizzled tile TMA wrote (no transpose pass), M=128 N=64 K=128, fp32 in TMEM
-//   epilogue tcgen05.ld O, scale by 1 / row sum, bf16, 128 contiguous bytes per row to ctx
-// Two softmax warpgroups ping-pong over two TMEM sets (2 x 256 columns) and a 3-slot shared
-// memory ring, so the MUFU-bound softmax of one item overlaps the loads and MMAs of the next.
+//   epilogue tcgen05.ld O, scale by 1 / row sum, bf16 into a 128-byte-swizzled staging box, one TMA store of
+//            the G*S x 64 box to ctx (r01d: direct 16-byte stores, 32 lines per instruction, were a third of
+//            the kernel: 0.42 ms with them, 0.27 ms without)
+// Two softmax warpgroups work on alternate items.  Each owns one S region in TMEM (128 columns; P
+// overwrites its first 64 once the row has been read) and two O regions (64 columns each), and runs
+// one item ahead of itself: softmax(j) -> epilogue(j - 2) -> softmax(j + 2) ..., so the P V MMA of item j and
+// the Q K^T MMA of item j + 2 (issued back to back: the tensor pipe executes them in order, which is what
+// protects P) run while the warpgroup drains the previous O.  r01c had one TMEM set per item and the
+// warpgroup idle across both MMA round trips: 49 % of DRAM peak.  A 4-slot shared-memory ring keeps the
+// loads of three items in flight.
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..5 / 6..9 softmax warpgroups 0 / 1 (TMEM lane quarter = warp % 4).
 //
 // Roofline: HBM (reads the 2304-wide qkv rows once, writes ctx once); the math is ~1 % of a layer.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,18 +43,18 @@ constexpr int H = 768;
 constexpr int HD = 64;
 constexpr int kHeads = 12;
 constexpr int kTile = 128;
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 constexpr int kTileBytes = kTile * HD * 2;  // 16 KiB
 constexpr int kSlotBytes = 3 * kTileBytes;  // Q, K, V
 constexpr int kThreads = 320;
 constexpr int kTmemCols = 512;
-constexpr int kSetCols = 256;  // S 128 | P 64 | O 64
-constexpr int kSmemBytes = kSlots * kSlotBytes + 1024 + 256;
+constexpr int kOBase = 256;    // TMEM columns: S/P of warpgroup 0 | S/P of warpgroup 1 | four O regions of 64
+constexpr int kSmemBytes = kSlots * kSlotBytes + 2 * kTileBytes /*ctx staging, one box per warpgroup*/ + 1024 + 256;
 
 struct AttParams {
   const int32_t* lens;
-  __nv_bfloat16* ctx;
   int B, S, G, tiles;
+  int dbg;  // ICD_ATTN_DBG (profiling only): 1 = skip the ctx stores, 2 = every item loads tile 0 (L2 hits)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -54,25 +62,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_ctx,
+                    const AttParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSlots * kSlotBytes);
-  uint64_t* full_bar = bars;             // [3] TMA landed
-  uint64_t* empty_bar = bars + 3;        // [3] P V of the item retired: slot reusable
-  uint64_t* sfull_bar = bars + 6;        // [2] S ready in TMEM
-  uint64_t* pready_bar = bars + 8;       // [2] P written by all 128 rows
-  uint64_t* ofull_bar = bars + 10;       // [2] O ready in TMEM
-  uint64_t* setfree_bar = bars + 12;     // [2] TMEM set drained by all 128 rows
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+  unsigned char* stage_o = smem + kSlots * kSlotBytes;  // [2 warpgroups][128 rows x 128 bytes], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_o + 2 * kTileBytes);
+  uint64_t* full_bar = bars;             // [4] TMA landed
+  uint64_t* empty_bar = bars + 4;        // [4] P V of the item retired: slot reusable
+  uint64_t* sfull_bar = bars + 8;        // [2] S ready in TMEM (per warpgroup)
+  uint64_t* pready_bar = bars + 10;      // [2] P written by all 128 rows (per warpgroup)
+  uint64_t* ofull_bar = bars + 12;       // [4] O ready in TMEM (per O region)
+  uint64_t* ofree_bar = bars + 16;       // [4] O region drained by all 128 rows
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int n_items = p.tiles * kHeads;
   const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_qkv);
+    ptx::prefetch_tmap(&tmap_ctx);
     for (int s = 0; s < kSlots; ++s) {
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
@@ -80,8 +97,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttParam
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&sfull_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&pready_bar[s]), 128);
+    }
+    for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(ptx::smem_u32(&ofull_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&setfree_bar[s]), 128);
+      ptx::mbar_init(ptx::smem_u32(&ofree_bar[s]), 128);
     }
     ptx::fence_mbar_init();
   }
@@ -100,7 +119,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttParam
       for (int j = 0; j < n_local; ++j) {
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
         const int tile = item / kHeads, head = item % kHeads;
-        const int row0 = tile * p.G * p.S;
+        const int row0 = (p.dbg & 2) ? 0 : tile * p.G * p.S;
         const int slot = j % kSlots;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), ((j / kSlots) & 1) ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
@@ -116,37 +135,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttParam
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(kTile, kTile);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(kTile, HD) | (1u << 16);  // B (= V) is MN-major
+      // item j: warpgroup w = j & 1, its i-th item (i = j >> 1); O region r = j & 3
       auto issue_s = [&](int j) {
-        const int slot = j % kSlots, set = j & 1;
+        const int slot = j % kSlots, w = j & 1;
         ptx::mbar_wait(ptx::smem_u32(&full_bar[slot]), (j / kSlots) & 1);
-        ptx::mbar_wait(ptx::smem_u32(&setfree_bar[set]), ((j >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t sq = ptx::smem_u32(smem + (size_t)slot * kSlotBytes);
         const uint32_t sk = sq + kTileBytes;
-        const uint32_t d = tmem_base + (uint32_t)(set * kSetCols);
+        const uint32_t d = tmem_base + (uint32_t)(w * kTile);
 #pragma unroll
         for (int k4 = 0; k4 < HD / 16; ++k4)
           ptx::mma_ss(d, ptx::make_desc_k128(sq + k4 * 32), ptx::make_desc_k128(sk + k4 * 32), idesc_s, k4 ? 1u : 0u);
-        ptx::tc_commit(ptx::smem_u32(&sfull_bar[set]));
+        ptx::tc_commit(ptx::smem_u32(&sfull_bar[w]));
       };
       auto issue_pv = [&](int j) {
-        const int slot = j % kSlots, set = j & 1;
-        ptx::mbar_wait(ptx::smem_u32(&pready_bar[set]), (j >> 1) & 1);
+        const int slot = j % kSlots, w = j & 1, i = j >> 1, r = j & 3;
+        ptx::mbar_wait(ptx::smem_u32(&pready_bar[w]), i & 1);
+        ptx::mbar_wait(ptx::smem_u32(&ofree_bar[r]), ((i >> 1) & 1) ^ 1);  // item j - 4 has left the O region
         ptx::tc_fence_after();
         const uint32_t sv = ptx::smem_u32(smem + (size_t)slot * kSlotBytes) + 2 * kTileBytes;
-        const uint32_t d = tmem_base + (uint32_t)(set * kSetCols + 192);
-        const uint32_t a = tmem_base + (uint32_t)(set * kSetCols + 128);
+        const uint32_t d = tmem_base + (uint32_t)(kOBase + r * HD);
+        const uint32_t a = tmem_base + (uint32_t)(w * kTile);
 #pragma unroll
         for (int ks = 0; ks < kTile / 16; ++ks)  // 16 keys per MMA: two 8-key groups, 1024 bytes apart
           ptx::mma_ts(d, a + (uint32_t)(ks * 8), ptx::make_desc_k128(sv + ks * 2048), idesc_o, ks ? 1u : 0u);
-        ptx::tc_commit(ptx::smem_u32(&ofull_bar[set]));
+        ptx::tc_commit(ptx::smem_u32(&ofull_bar[r]));
         ptx::tc_commit(ptx::smem_u32(&empty_bar[slot]));
       };
+      if (n_local > 0) issue_s(0);
+      if (n_local > 1) issue_s(1);
       for (int j = 0; j < n_local; ++j) {
-        issue_s(j);
-        if (j > 0) issue_pv(j - 1);
+        issue_pv(j);
+        // S of the warpgroup's next item overwrites the P just consumed: issued behind P V on the same pipe
+        if (j + 2 < n_local) issue_s(j + 2);
       }
-      if (n_local > 0) issue_pv(n_local - 1);
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -156,88 +178,157 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttParam
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
     const int g = r / p.S;
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e): softmax in base 2
+    const uint32_t s_addr = lane_addr + (uint32_t)(wg * kTile);  // this warpgroup's S region; P = its first 64 columns
+    // epilogue of an earlier item: O from TMEM, scale by 1 / row sum, bf16 into the warpgroup's staging box
+    // (row = 128 bytes, 16-byte chunk c at chunk c ^ (row & 7): conflict-free), one TMA store of the box
+    unsigned char* my_stage = stage_o + wg * kTileBytes;
+    const uint32_t stage_u32 = ptx::smem_u32(my_stage);
+    unsigned char* my_row = my_stage + r * 128;
+    const int sw = r & 7;
+    const bool leader = quarter == 0 && lane == 0;
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); };
+    auto epilogue = [&](int j, float inv, int row0, int head) {
+      const int rgn = j & 3;
+      ptx::mbar_wait(ptx::smem_u32(&ofull_bar[rgn]), (uint32_t)(j >> 2) & 1);
+      ptx::tc_fence_after();
+      uint32_t ov[HD];
+      const uint32_t o_addr = lane_addr + (uint32_t)(kOBase + rgn * HD);
+      ptx::tmem_ld_32x32b_x32(o_addr, ov);
+      ptx::tmem_ld_32x32b_x32(o_addr + 32, ov + 32);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(ptx::smem_u32(&ofree_bar[rgn]));
+      if (leader) ptx::tma_store_wait_read<0>();  // the previous box of this warpgroup has left shared memory
+      wg_sync();
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(ov[c * 8 + 0]) * inv, __uint_as_float(ov[c * 8 + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(ov[c * 8 + 2]) * inv, __uint_as_float(ov[c * 8 + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(ov[c * 8 + 4]) * inv, __uint_as_float(ov[c * 8 + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(ov[c * 8 + 6]) * inv, __uint_as_float(ov[c * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
+      }
+      ptx::fence_proxy_async_smem();
+      wg_sync();
+      if (leader && !(p.dbg & 1)) {
+        // the box is G * S rows tall (the rows this tile owns); rows past the end of the buffer are clipped
+        ptx::tma_store_2d(&tmap_ctx, stage_u32, head * HD, row0);
+        ptx::tma_store_commit();
+      }
+    };
+    int prev = -1, prev_row0 = 0, prev_head = 0;
+    float prev_inv = 0.f;
+    // the sequence length of this row for item j, requested one item ahead
+    auto load_len = [&](int j) {
+      const int item = (int)blockIdx.x + j * (int)gridDim.x;
+      const int seq = (item / kHeads) * p.G + g;
+      return (j < n_local && g < p.G && seq < p.B) ? __ldg(p.lens + seq) : 0;
+    };
+    int next_len = load_len(wg);
     for (int j = wg; j < n_local; j += 2) {
       const int item = (int)blockIdx.x + j * (int)gridDim.x;
       const int tile = item / kHeads, head = item % kHeads;
-      const int set = j & 1;
       const uint32_t par = (uint32_t)(j >> 1) & 1;
       const int seq = tile * p.G + g;
       const bool row_used = g < p.G && seq < p.B;
-      const int len = row_used ? min(p.lens[seq], p.S) : 0;
+      const int len = row_used ? min(next_len, p.S) : 0;
+      next_len = load_len(j + 2);
       const int lo = g * p.S, hi = lo + len;  // key columns this row attends to
       const bool q_live = row_used && (r - lo) < len;
-      const int wlo = __reduce_min_sync(0xffffffffu, lo);
-      const int whi = __reduce_max_sync(0xffffffffu, hi);
+      // warp-uniform view of the key range: a 32-column chunk is `live` if some row of the warp needs it and
+      // `full` if every row needs all of it (then no per-element mask: the common case of unpadded sequences)
+      const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+      const int wlo_max = __reduce_max_sync(0xffffffffu, lo), whi_min = __reduce_min_sync(0xffffffffu, hi);
 
-      ptx::mbar_wait(ptx::smem_u32(&sfull_bar[set]), par);
+      ptx::mbar_wait(ptx::smem_u32(&sfull_bar[wg]), par);
       ptx::tc_fence_after();
-      const uint32_t s_addr = lane_addr + (uint32_t)(set * kSetCols);
-      uint32_t sv[kTile];
+      // Two passes over the row, 64 columns (two chunks) at a time, re-reading S from TMEM for the second one: keeping
+      // all 128 scores in registers cost 340 bytes of spills per thread, and TMEM reads are cheap.  Pass 2 writes P
+      // chunk c (16 packed columns at 16 c) over S columns that this pass has already pulled into registers.
+      auto live = [&](int c32) { return c32 * 32 < whi && c32 * 32 + 32 > wlo; };
+      auto full = [&](int c32) { return c32 * 32 >= wlo_max && c32 * 32 + 32 <= whi_min; };
+      auto masked = [&](uint32_t bits, int col) {
+        return (col >= lo && col < hi) ? __uint_as_float(bits) : -INFINITY;
+      };
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: the reduction is latency-bound
+#pragma unroll 1
+      for (int h2 = 0; h2 < 2; ++h2) {
+        if (!live(2 * h2) && !live(2 * h2 + 1)) continue;
+        uint32_t sv[64];
+        ptx::tmem_ld_32x32b_x32(s_addr + h2 * 64, sv);  // both chunks of a live pair: a dead one costs nothing to read
+        ptx::tmem_ld_32x32b_x32(s_addr + h2 * 64 + 32, sv + 32);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c32 = 0; c32 < 4; ++c32) {
-        if (c32 * 32 < whi && c32 * 32 + 32 > wlo) {  // warp-uniform: some row of this warp needs the chunk
-          ptx::tmem_ld_32x32b_x32(s_addr + c32 * 32, sv + c32 * 32);
-        } else {
+        for (int q = 0; q < 2; ++q) {
+          const int c32 = 2 * h2 + q;
+          if (!live(c32)) continue;
+          if (full(c32)) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) sv[c32 * 32 + c] = 0xff800000u;  // -inf
+            for (int c = 0; c < 32; ++c) m4[c & 3] = fmaxf(m4[c & 3], __uint_as_float(sv[q * 32 + c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) m4[c & 3] = fmaxf(m4[c & 3], masked(sv[q * 32 + c], c32 * 32 + c));
+          }
         }
       }
-      ptx::tmem_ld_wait();
-      float m = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kTile; ++c) {
-        const float v = (c >= lo && c < hi) ? __uint_as_float(sv[c]) : -INFINITY;
-        sv[c] = __float_as_uint(v);
-        m = fmaxf(m, v);
-      }
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       const float msc = (m == -INFINITY) ? 0.f : m * sc;
-      float sum = 0.f;
-      const uint32_t p_addr = s_addr + 128;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t pk[32];
+        if (live(2 * h2) || live(2 * h2 + 1)) {
+          uint32_t sv[64];
+          ptx::tmem_ld_32x32b_x32(s_addr + h2 * 64, sv);
+          ptx::tmem_ld_32x32b_x32(s_addr + h2 * 64 + 32, sv + 32);
+          ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {  // 32 keys -> 16 packed columns
-        uint32_t pk[16];
-        if (c16 * 32 < whi && c16 * 32 + 32 > wlo) {
+          for (int q = 0; q < 2; ++q) {
+            const int c32 = 2 * h2 + q;
+            if (!live(c32)) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float e0 = exp2f(fmaf(__uint_as_float(sv[c16 * 32 + 2 * c]), sc, -msc));
-            const float e1 = exp2f(fmaf(__uint_as_float(sv[c16 * 32 + 2 * c + 1]), sc, -msc));
-            sum += e0 + e1;
-            pk[c] = pack_bf16(e0, e1);
+              for (int c = 0; c < 16; ++c) pk[q * 16 + c] = 0u;
+            } else if (full(c32)) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const float e0 = ex2_approx(fmaf(__uint_as_float(sv[q * 32 + 2 * c]), sc, -msc));
+                const float e1 = ex2_approx(fmaf(__uint_as_float(sv[q * 32 + 2 * c + 1]), sc, -msc));
+                sum4[c & 3] += e0 + e1;
+                pk[q * 16 + c] = pack_bf16(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {  // masked entries are -inf: ex2 gives 0
+                const float e0 = ex2_approx(fmaf(masked(sv[q * 32 + 2 * c], c32 * 32 + 2 * c), sc, -msc));
+                const float e1 = ex2_approx(fmaf(masked(sv[q * 32 + 2 * c + 1], c32 * 32 + 2 * c + 1), sc, -msc));
+                sum4[c & 3] += e0 + e1;
+                pk[q * 16 + c] = pack_bf16(e0, e1);
+              }
+            }
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = 0u;
+          for (int c = 0; c < 32; ++c) pk[c] = 0u;
         }
-        ptx::tmem_st_32x32b_x16(p_addr + c16 * 16, pk);
+        ptx::tmem_st_32x32b_x16(s_addr + h2 * 32, pk);
+        ptx::tmem_st_32x32b_x16(s_addr + h2 * 32 + 16, pk + 16);
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ptx::smem_u32(&pready_bar[set]));
+      ptx::mbar_arrive(ptx::smem_u32(&pready_bar[wg]));
 
-      ptx::mbar_wait(ptx::smem_u32(&ofull_bar[set]), par);
-      ptx::tc_fence_after();
-      uint32_t ov[HD];
-      ptx::tmem_ld_32x32b_x32(s_addr + 192, ov);
-      ptx::tmem_ld_32x32b_x32(s_addr + 224, ov + 32);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(ptx::smem_u32(&setfree_bar[set]));
-
-      if (row_used) {
-        // padded query positions are never read downstream (masked keys, masked pooling): zeros
-        const float inv = (q_live && sum > 0.f) ? 1.0f / sum : 0.f;
-        __nv_bfloat16* orow = p.ctx + ((size_t)tile * p.G * p.S + r) * H + head * HD;
-#pragma unroll
-        for (int c = 0; c < HD / 8; ++c) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(ov[c * 8 + 0]) * inv, __uint_as_float(ov[c * 8 + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(ov[c * 8 + 2]) * inv, __uint_as_float(ov[c * 8 + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(ov[c * 8 + 4]) * inv, __uint_as_float(ov[c * 8 + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(ov[c * 8 + 6]) * inv, __uint_as_float(ov[c * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 8) = o;
-        }
-      }
+      // while P V (j) and Q K^T (j + 2) run: drain the previous item of this warpgroup
+      if (prev >= 0) epilogue(prev, prev_inv, prev_row0, prev_head);
+      prev = j;
+      // padded query positions are never read downstream (masked keys, masked pooling): zeros
+      prev_inv = (q_live && sum > 0.f) ? 1.0f / sum : 0.f;
+      prev_row0 = tile * p.G * p.S;
+      prev_head = head;
     }
+    if (prev >= 0) epilogue(prev, prev_inv, prev_row0, prev_head);
+    if (leader) ptx::tma_store_wait_all();  // global writes complete before the kernel ends
   }
 
   ptx::tc_fence_before();
@@ -254,23 +345,32 @@ int attention_make_map(void* map128, const void* qkv, int64_t rows) {
   return make_tmap_bf16_2d(map128, qkv, (uint64_t)rows, (uint64_t)(3 * H), kTile, HD, true);
 }
 
-int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx, cudaStream_t st) {
+int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx, int64_t ctx_rows,
+                        cudaStream_t st) {
   if (S < 1 || S > kTile) {
     set_error("attention: S=%d outside [1, 128]", S);
     return ICD_E_UNSUPPORTED;
   }
   AttParams p{};
   p.lens = lens;
-  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
   p.B = B;
   p.S = S;
   p.G = kTile / S;
   p.tiles = (B + p.G - 1) / p.G;
+  {
+    static const int dbg = getenv("ICD_ATTN_DBG") ? atoi(getenv("ICD_ATTN_DBG")) : 0;
+    p.dbg = dbg;
+  }
   CUtensorMap tm;
   memcpy(&tm, tmap_qkv, sizeof(tm));
+  // ctx store box: the G * S rows a tile owns x one head (64 columns); encoded per launch because it depends on S
+  alignas(128) unsigned char ctx_map[128];
+  ICD_TRY(make_tmap_bf16_2d(ctx_map, ctx, (uint64_t)ctx_rows, (uint64_t)H, (uint32_t)(p.G * S), HD, true));
+  CUtensorMap tc;
+  memcpy(&tc, ctx_map, sizeof(tc));
   ICD_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int grid = std::min(p.tiles * kHeads, kSMs);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm, p);
+  attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm, tc, p);
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;

@@ -41,7 +41,9 @@ int launch_layernorm(const void* x_bf16, int M, const float* gamma, const float*
 int launch_attention(const void* qkv_bf16, const int32_t* lens, int B, int S, void* ctx_bf16, cudaStream_t st);
 // attention_tc.cu: the same on tensor cores (tcgen05); tmap_qkv from attention_make_map over the [rows, 2304] buffer
 int attention_make_map(void* map128, const void* qkv_bf16, int64_t rows);
-int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx_bf16, cudaStream_t st);
+// ctx_rows = rows of the ctx buffer (a multiple of 128 >= B*S): the store boxes are clipped against it
+int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx_bf16, int64_t ctx_rows,
+                        cudaStream_t st);
 // masked mean over tokens + L2 normalise -> [B,768] (fp32 or bf16)
 int launch_pool_normalise(const void* h_bf16, const int32_t* lens, int B, int S, void* out, int out_dtype,
                           cudaStream_t st);

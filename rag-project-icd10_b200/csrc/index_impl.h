@@ -33,8 +33,12 @@ struct icd_index {
   int map_gen = -1;
   // workspace
   icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage, gbound;
-  // stage timing (scan, merge, finalise)
-  cudaEvent_t ev[4];
+  // stage timing (scan, merge, finalise): a ring of event quads so that back-to-back searches can be averaged
+  // afterwards without a host sync between them (bench.py's roofline figure); ev = the quad of the current call
+  static constexpr int kTimingRing = 64;
+  cudaEvent_t ev_ring[kTimingRing][4];
+  cudaEvent_t* ev = ev_ring[0];
+  int64_t timed_calls = 0;   // searches recorded since timing was switched on
   bool timing = false, timing_pending = false;
   int last_launches = 0;
 };

@@ -108,3 +108,10 @@ class VectorIndex:
         launches = C.c_int()
         N.check(N.lib().icd_index_last_timing(self._h, us, C.byref(launches)), "icd_index_last_timing")
         return {"scan_us": us[0], "merge_us": us[1], "finalise_us": us[2], "launches": launches.value}
+
+    def mean_timing(self):
+        """Stage times averaged over the searches since set_timing(True) (most recent 64)."""
+        us = (C.c_float * 3)()
+        calls = C.c_int()
+        N.check(N.lib().icd_index_mean_timing(self._h, us, C.byref(calls)), "icd_index_mean_timing")
+        return {"scan_us": us[0], "merge_us": us[1], "finalise_us": us[2], "calls": calls.value}
