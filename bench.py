@@ -174,6 +174,37 @@ def cpu_sample(rows, batch, reps=1):
     return dt
 
 
+def cpu_encoder_sample(n_sent=256, seq=64, batch=32):
+    """The reference's CPU encoder path (SentenceTransformer.encode restated: HF BertModel fp32 + masked mean +
+    L2 normalise, oracle/encoder.py) on a bounded sample: n_sent synthetic sentences of `seq` tokens in batches of
+    32 (encode_batch's batch_size, embedding_service.py:97-102), all host threads."""
+    cores = _use_all_host_threads()
+    import torch
+    torch.set_num_threads(cores)
+    from transformers import BertModel
+    from oracle import encoder as oenc
+    torch.manual_seed(0)
+    model = BertModel(oenc.bert_config(12, 21128, 512), add_pooling_layer=False).eval()
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(1000, 21128, (n_sent, seq), generator=g)
+    ids[:, 0], ids[:, -1] = 101, 102
+    mask = torch.ones_like(ids)
+
+    def run():
+        with torch.no_grad():
+            for lo in range(0, n_sent, batch):
+                h = model(input_ids=ids[lo:lo + batch], attention_mask=mask[lo:lo + batch]).last_hidden_state
+                m = mask[lo:lo + batch].unsqueeze(-1).float()
+                torch.nn.functional.normalize((h * m).sum(1) / m.sum(1).clamp(min=1e-9), p=2, dim=1)
+    run()   # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    return {"value": n_sent / dt, "unit": "sentences/s", "cores": cores, "kind": "port",
+            "sample": f"{n_sent} synthetic sentences x {seq} tokens, batch {batch}, 12-layer HF BertModel fp32 "
+                      f"(oracle/encoder.py arithmetic), torch {torch.get_num_threads()} threads"}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path (restated: numpy
     fp32 exact IP + top-k; pymilvus/milvus-lite are not installable offline), host cores only."""
@@ -206,6 +237,13 @@ def run_reference(args, rank, world):
                                    f"top-k, oracle/search.py::fast_topk), extrapolated linearly in rows to {total_rows}"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_encoder:
+        try:
+            cb = cpu_encoder_sample()
+            line["encoder"] = {"metric": "text2vec sentences/sec", "value": cb["value"], "unit": "sentences/s",
+                               "batch": 32, "seq_len": 64, "layers": 12, "dtype": "f32", "cpu_baseline": cb}
+        except Exception as e:
+            line["encoder"] = {"error": repr(e)[:200]}
     emit(line)
 
 
@@ -434,7 +472,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "rows": rows_total, "rows_per_gpu": rows_local, "dim": DIM, "batch": B,
-                       "k": k, "weight_mode": "rerank", "l2": "corpus >> L2 (no flush needed)",
+                       "k": k, "weight_mode": "rerank", "l2": "corpus >> L2 (no flush needed)", "tune": args.tune or None,
                        "exchange": ("peer-store" if args.exchange else "nccl-allgather") if world > 1 else None},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 2,
                     "d2h_bytes_per_step": B * k * 16},
@@ -449,6 +487,11 @@ def main():
                 "sample": f"{args.cpu_batch} queries x {args.cpu_rows} rows (numpy fp32 GEMM + argpartition top-k, "
                           f"oracle/search.py::fast_topk), extrapolated linearly in rows to {rows_total}"}
         if enc is not None:
+            if not args.no_cpu_baseline and world == 1 and "error" not in enc:
+                try:
+                    enc["cpu_baseline"] = cpu_encoder_sample()
+                except Exception as e:
+                    enc["cpu_baseline"] = {"error": repr(e)[:200]}
             line["encoder"] = enc
         emit(line)
     if world > 1:

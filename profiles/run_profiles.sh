@@ -27,6 +27,6 @@ $NCU --set full --import-source on -k regex:scan_stream -s 1 -c 1 -f -o $OUT/${T
 # encoder: one layer's worth of kernels of the second forward (1 + 12*7 + 1 launches per forward)
 ENC_REPS=2 $NCU --set full --import-source on -k regex:'gemm_tc|attention|layernorm' -s 93 -c 7 -f -o $OUT/${TAG}_encoder_layer \
     python profiles/encoder_once.py > $OUT/${TAG}_ncu_encoder.log 2>&1
-ENC_REPS=2 $NCU --metrics gpu__time_duration.sum -k regex:'gemm_tc|attention|layernorm|embed|pool' -s 86 -c 86 --csv \
+ENC_REPS=2 $NCU --metrics gpu__time_duration.sum -k regex:'gemm_tc|attention|layernorm|embed|pool' -s 63 -c 63 --csv \
     --log-file $OUT/${TAG}_encoder_launches.csv python profiles/encoder_once.py > /dev/null 2>&1
 ls -la $OUT

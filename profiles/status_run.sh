@@ -12,7 +12,7 @@ tail -n 3 $OUT/${TAG}_smoke.log
 cat $OUT/${TAG}_bench.json
 ( time python bench.py --impl reference --steps 2 --warmup 1 ) > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
 cat $OUT/${TAG}_bench_ref.json
-ENC_REPS=2 ncu --clock-control none --metrics gpu__time_duration.sum -k regex:'gemm_tc|attention|layernorm|embed|pool' -s 86 -c 86 --csv \
+ENC_REPS=2 ncu --clock-control none --metrics gpu__time_duration.sum -k regex:'gemm_tc|attention|layernorm|embed|pool' -s 63 -c 63 --csv \
     --log-file $OUT/${TAG}_encoder_launches.csv python profiles/encoder_once.py > /dev/null 2>&1
 if [ "${2:-}" = "sweep" ]; then
 for B in 1 8 32 128 256 1024 4096; do

@@ -15,8 +15,14 @@
 //     N must be >= 128: with A in TMEM every MMA re-reads the 128x16 A slice (4 KiB) at the
 //     TMEM read rate, ~64 cycles, so N=64 (32 cycles of math) runs the pipe at half rate
 //     (measured: 38 % tensor-active with N=64).  The accumulators take the columns Q leaves
-//     free: one buffer for dim=768 (the epilogue drains it to registers at once and hands it
-//     back), two for dim <= 512.
+//     free.  For dim = 768 the tile fills 384 columns and leaves room for ONE 128-column buffer: the MMAs
+//     of tile i+1 wait until the epilogue has drained tile i (64 KiB through the same 64 B/clk TMEM read
+//     path the A operand uses, ~1 k cycles per 3 k-cycle tile: r01b measured 70 % tensor-active at
+//     B = 1024).  In the tensor-bound regime (>= 2 query tiles per row stream) the last third of K
+//     therefore lives in SHARED memory instead (64 KiB, canonical K-major 128-byte-swizzle tiles, SS
+//     MMAs for those K blocks): Q then takes 256 TMEM columns, two accumulator buffers fit, and the
+//     drain of tile i overlaps the MMAs of tile i+1.  The HBM-bound regime keeps the whole tile in
+//     TMEM and all of shared memory for the row stream.
 //   * epilogue: thread == TMEM lane == query.  It reads its 64 scores with tcgen05.ld,
 //     compares against its private k-th best (a register) and only on the rare hit inserts
 //     into its private sorted list in shared memory.  Level weights (ICD_WEIGHT_PRE) are
@@ -67,6 +73,7 @@ struct ScanParams {
   int kbs;       // K blocks (128 x 64 tiles) per stage; divides nkb
   int nacc;      // accumulator buffers (1 or 2) in the TMEM columns behind the query tile
   int acc_col0;  // first accumulator column (== dim / 2 rounded up to 128)
+  int nkb_tmem;  // K blocks of the query tile held in TMEM; the remaining nkb - nkb_tmem live in shared memory
   int tstride;   // scan every tstride-th row tile only (1 = all rows; > 1 = the sampling pre-pass)
   int* progress; // [G * T] tiles issued by each CTA's producer (drift limiter), or null
   int drift;     // a producer may run at most this many tiles ahead of the slowest CTA of its row group
@@ -101,7 +108,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   // shared memory carve-up
   const int stage_bytes = p.kbs * kBoxBytes;
   unsigned char* stage_base = smem;                                           // nst stages, 1024-aligned
-  float* list_s = reinterpret_cast<float*>(smem + (size_t)p.nst * stage_bytes);  // [kc][BM]
+  unsigned char* q_tail = smem + (size_t)p.nst * stage_bytes;  // (nkb - nkb_tmem) tiles of 128 queries x 64 bf16, 1024-aligned
+  constexpr int kQTileBytes = BM * BK * 2;                      // 16 KiB
+  float* list_s = reinterpret_cast<float*>(q_tail + (size_t)(p.nkb - p.nkb_tmem) * kQTileBytes);  // [kc][BM]
   int* list_i = reinterpret_cast<int*>(list_s + (size_t)p.kc * BM);           // [kc][BM]
   uint64_t* bars = reinterpret_cast<uint64_t*>(list_i + (size_t)p.kc * BM);
   uint64_t* full_bar = bars;                    // [nst]
@@ -148,7 +157,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       my_s[j * BM] = -INFINITY;
       my_i[j * BM] = -1;
     }
-    // query tile -> TMEM: lane = query, 32-bit column c holds elements (2c, 2c+1)
+    // query tile -> TMEM: lane = query, 32-bit column c holds elements (2c, 2c+1); K blocks >= nkb_tmem go to
+    // shared memory as K-major tiles in the 128-byte-swizzle canonical layout (row = query, 16-byte chunk c of the
+    // row at chunk c ^ (row & 7)), the layout the SS MMA descriptor expects
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const uint4* qrow = reinterpret_cast<const uint4*>(p.q + (size_t)query * p.dim);
     for (int c16 = 0; c16 < p.dim / 32; ++c16) {  // 16 columns = 32 bf16 = 4 x uint4
@@ -166,9 +177,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
         for (int v = 0; v < 16; ++v) r[v] = 0u;
       }
-      ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(c16 * 16), r);
+      const int kb = c16 >> 1;  // 64 bf16 per K block = two 32-element halves
+      if (kb < p.nkb_tmem) {
+        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(c16 * 16), r);
+      } else {
+        unsigned char* row = q_tail + (size_t)(kb - p.nkb_tmem) * kQTileBytes + ep_lane * 128;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int chunk = (c16 & 1) * 4 + v;
+          *reinterpret_cast<uint4*>(row + ((chunk ^ (ep_lane & 7)) << 4)) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+        }
+      }
     }
     ptx::tmem_st_wait();
+    ptx::fence_proxy_async_smem();  // the tail tiles are read by the tensor core (async proxy)
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -221,6 +243,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     // ===================== MMA issuer =====================
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+      const uint64_t qtail_desc0 = ptx::make_desc_k128(ptx::smem_u32(q_tail));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -240,8 +263,13 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // +2 per 32 bytes of K inside the 128-byte swizzle row, +512 per 8 KiB tile (16-byte units)
               const uint64_t bdesc = desc0 + (uint64_t)(j * (kBoxBytes >> 4) + k4 * 2);
-              const uint32_t a_tmem = tmem_base + (uint32_t)(((kb + j) * (BK / 16) + k4) * 8);
-              ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+              if (kb + j < p.nkb_tmem) {
+                const uint32_t a_tmem = tmem_base + (uint32_t)(((kb + j) * (BK / 16) + k4) * 8);
+                ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+              } else {
+                const uint64_t adesc = qtail_desc0 + (uint64_t)((kb + j - p.nkb_tmem) * (kQTileBytes >> 4) + k4 * 2);
+                ptx::mma_ss(d_tmem, adesc, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+              }
             }
           }
           ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // frees the stage when the MMAs retire
@@ -340,8 +368,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   }
 }
 
-size_t smem_bytes(int bn, int nst, int kbs, int kc) {
-  return (size_t)nst * kbs * (bn * BK * 2) + (size_t)kc * BM * 8 + (2 * kMaxStages + 4) * 8 + 16;
+size_t smem_bytes(int bn, int nst, int kbs, int kc, int q_tail_tiles) {
+  return (size_t)nst * kbs * (bn * BK * 2) + (size_t)q_tail_tiles * (BM * BK * 2) + (size_t)kc * BM * 8 +
+         (2 * kMaxStages + 4) * 8 + 16;
 }
 
 }  // namespace
@@ -413,13 +442,14 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, sample, gen;
+  int bn, drift, tmax, kbs, sample, qsplit, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
     tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 8)));
     kbs = std::min(3, std::max(1, env_int("ICD_SCAN_KBS", 2)));
     sample = env_int("ICD_SCAN_SAMPLE", -1);
+    qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always
     gen = 0;
   }
 };
@@ -438,6 +468,7 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_tmax")) t.tmax = std::min(32, std::max(1, value));
   else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(3, std::max(1, value));
   else if (!strcmp(key, "scan_sample")) t.sample = value;
+  else if (!strcmp(key, "scan_qsplit")) t.qsplit = value;
   else return ICD_E_ARG;
   ++t.gen;  // tensor maps depend on bn / kbs: indexes rebuild theirs when the generation moves
   return ICD_OK;
@@ -485,15 +516,22 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   G = std::min(G, a.P);
   *a.groups_used = G;
 
+  // Query tile placement: all of K in TMEM, or (tensor-bound launches, dim wider than 512) the K blocks that do not
+  // leave room for a second accumulator buffer in shared memory.
+  const int nkb = a.dim / BK;
+  const int nkb_fit2 = (kTmemCols - 2 * BN) / (BK / 2);  // K blocks that fit beside two BN-column accumulators
+  const bool split = tun().qsplit > 0 || (tun().qsplit < 0 && T_launch >= 2);
+  const int nkb_tmem = (split && nkb > nkb_fit2 && BN == 128) ? nkb_fit2 : nkb;
+  const int q_tail_tiles = nkb - nkb_tmem;
   // pipeline depth from the shared memory left after the per-thread lists
   const int kbs = stage_kblocks(a.dim);
   int nst = kMaxStages;
-  while (nst > 2 && smem_bytes(BN, nst, kbs, a.k) > (size_t)kSmemLimit) --nst;
-  if (smem_bytes(BN, nst, kbs, a.k) > (size_t)kSmemLimit) {
+  while (nst > 2 && smem_bytes(BN, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) --nst;
+  if (smem_bytes(BN, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) {
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
-  const size_t smem = smem_bytes(BN, nst, kbs, a.k);
+  const size_t smem = smem_bytes(BN, nst, kbs, a.k, q_tail_tiles);
   ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   CUtensorMap tmap;
   memcpy(&tmap, map128, sizeof(CUtensorMap));
@@ -516,7 +554,8 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.qt0 = qt0;
     p.nst = nst;
     p.kbs = kbs;
-    p.acc_col0 = ((a.dim / 2 + 127) / 128) * 128;
+    p.nkb_tmem = nkb_tmem;
+    p.acc_col0 = ((nkb_tmem * (BK / 2) + 127) / 128) * 128;
     p.nacc = (kTmemCols - p.acc_col0) / BN >= 2 ? 2 : 1;
     p.tstride = tstride;
     p.drift = scan_drift();

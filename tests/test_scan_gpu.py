@@ -213,11 +213,13 @@ def test_full_size_properties(pkg, native):
 
 
 @pytest.mark.parametrize("knobs", [dict(scan_sample=4), dict(scan_sample=3, scan_drift=1), dict(scan_sample=0, scan_drift=0),
-                                   dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=3)])
+                                   dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=3),
+                                   dict(scan_qsplit=0), dict(scan_qsplit=1, scan_sample=4), dict(scan_qsplit=1, scan_tmax=1)])
 @pytest.mark.parametrize("weight_mode", [2, 1])
 def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
     """The sampling pre-pass (admission bound from every s-th row tile), the drift limiter and the
-    launch shaping are performance devices: with any setting the tensor scan returns the oracle's
+    launch shaping and the placement of the query tile (all of K in tensor memory, or its last third in shared
+    memory so that two accumulator buffers fit) are performance devices: with any setting the tensor scan returns the oracle's
     top-k.  Forced on here at sizes the oracle finishes in seconds (by default the pre-pass
     only runs on tables of >= 2 M rows)."""
     n, B, k, dim = 60000, 300, 10, 768
@@ -232,7 +234,7 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         native.tune(**knobs)
         score, raw, ids = idx.search(q, k, weight_mode=weight_mode, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2, scan_qsplit=-1)
     if weight_mode == native.WEIGHT_PRE:
         w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
         full = (q @ corpus.T) * w[None, :]
