@@ -32,6 +32,15 @@
 //     the bound the other row groups have proven; without it each of the 148 row groups warms
 //     its own lists and the insert path, not HBM, bounds the kernel (ncu, B=128: 42 % of
 //     epilogue samples in the insert loop, 57 % DRAM utilisation).
+//   * CTA pairs (NC = 2, launches with an even number of query tiles): two CTAs of one TPC hold
+//     neighbouring query tiles and run ONE tcgen05.mma.cta_group::2 (M = 256 queries, N = 128 rows) per K
+//     step, issued by the pair's leader.  Each CTA loads only HALF of every row tile (64 rows) and the tensor
+//     cores read both halves, so the shared-memory port carries half the fill and half the B reads per SM
+//     (with TMA fill 64 B/clk + B reads 64 B/clk + the shared-memory third of Q the single-CTA form asks
+//     117 % of the 128 B/clk port) and the L2 -> SM traffic of the row stream halves as well.  Measured
+//     (r01d, 10 M rows): B = 256 0.707 -> 0.750 of sustained bf16 peak, B = 1024 and 4096 unchanged within
+//     noise (0.83 / 0.79: those run into the 1 kW power cap at ~1.66 GHz, not into a port).
+//     ICD_SCAN_QTMEM=6 keeps half of K in shared memory instead of a third: no better.
 //   * grid = G row groups x T query tiles; each CTA writes one sorted list per query to the
 //     partial buffer [B, G, k] that topk_merge.cu reduces.
 //
@@ -95,11 +104,12 @@ __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, i
   return ls[(kc - 1) * BM];
 }
 
-// BN = table rows per accumulator tile (MMA N)
-template <int BN>
+// BN = table rows per accumulator tile (MMA N); NC = CTAs per MMA (2 = CTA pair, cta_group::2)
+template <int BN, int NC>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-  constexpr int kBoxBytes = BN * BK * 2;  // one BN x 64 bf16 tile
+  constexpr int kBoxBytes = (BN / NC) * BK * 2;  // this CTA's share of one BN x 64 bf16 tile
+  const uint32_t rank = NC == 2 ? ptx::cluster_ctarank() : 0u;  // 0 = the pair's leader (issues the MMAs)
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x / p.T;
@@ -132,16 +142,21 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[b]), 1);
-      ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), 4);  // one arrival per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[b]), 4 * NC);  // one arrival per epilogue warp of every CTA of the MMA
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_holder), kTmemCols);
-    ptx::tmem_relinquish();
+    if (NC == 2) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_holder), kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_holder), kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NC == 2) ptx::cluster_sync(); else __syncthreads();  // barriers of both CTAs are initialised from here on
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
@@ -193,7 +208,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     ptx::fence_proxy_async_smem();  // the tail tiles are read by the tensor core (async proxy)
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (NC == 2) ptx::cluster_sync(); else __syncthreads();  // the leader's MMAs read BOTH CTAs' query tiles
   ptx::tc_fence_after();
 
   if (warp == 0) {
@@ -224,12 +239,20 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
       }
       if (lane == 0) {
-        const int row = (int)(t * p.tstride * BN);
+        const int row = (int)(t * p.tstride * BN) + (int)rank * (BN / NC);  // this CTA's rows of the tile
         for (int kb = 0; kb < p.nkb; kb += p.kbs) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
-          ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
-          ptx::tma_load_3d(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
+          if (NC == 1) {
+            const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
+            ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
+            ptx::tma_load_3d(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
+          } else {
+            // both CTAs' bytes are counted on the LEADER's barrier (only its MMA thread waits for the stage)
+            if (rank == 0) ptx::mbar_expect_tx(ptx::smem_u32(&full_bar[stage]), 2u * (uint32_t)stage_bytes);
+            const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+            ptx::tma_load_3d_pair(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
+          }
+
           if (++stage == p.nst) {
             stage = 0;
             phase ^= 1;
@@ -241,8 +264,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (prog && lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + me), "r"(0x7fffffff) : "memory");
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    if (rank == 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * NC, BN);
       const uint64_t qtail_desc0 = ptx::make_desc_k128(ptx::smem_u32(q_tail));
       int stage = 0;
       uint32_t phase = 0;
@@ -263,22 +286,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               // +2 per 32 bytes of K inside the 128-byte swizzle row, +512 per 8 KiB tile (16-byte units)
               const uint64_t bdesc = desc0 + (uint64_t)(j * (kBoxBytes >> 4) + k4 * 2);
+              const uint32_t acc_flag = (kb | j | k4) ? 1u : 0u;
               if (kb + j < p.nkb_tmem) {
                 const uint32_t a_tmem = tmem_base + (uint32_t)(((kb + j) * (BK / 16) + k4) * 8);
-                ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+                if (NC == 1) ptx::mma_ts(d_tmem, a_tmem, bdesc, idesc, acc_flag);
+                else ptx::mma_ts_pair(d_tmem, a_tmem, bdesc, idesc, acc_flag);
               } else {
                 const uint64_t adesc = qtail_desc0 + (uint64_t)((kb + j - p.nkb_tmem) * (kQTileBytes >> 4) + k4 * 2);
-                ptx::mma_ss(d_tmem, adesc, bdesc, idesc, (kb | j | k4) ? 1u : 0u);
+                if (NC == 1) ptx::mma_ss(d_tmem, adesc, bdesc, idesc, acc_flag);
+                else ptx::mma_ss_pair(d_tmem, adesc, bdesc, idesc, acc_flag);
               }
             }
           }
-          ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));  // frees the stage when the MMAs retire
+          // frees the stage (in both CTAs) when the MMAs retire
+          if (NC == 1) ptx::tc_commit(ptx::smem_u32(&empty_bar[stage]));
+          else ptx::tc_commit_pair(ptx::smem_u32(&empty_bar[stage]), 3);
           if (++stage == p.nst) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));  // accumulator tile complete
+        // accumulator tile complete (each CTA's epilogue drains its own 128 queries)
+        if (NC == 1) ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));
+        else ptx::tc_commit_pair(ptx::smem_u32(&tfull_bar[buf]), 3);
       }
     }
   } else {
@@ -311,7 +341,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+      if (lane == 0) {
+        if (NC == 1) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+        else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[buf]), 0));  // the leader's barrier
+      }
 
       const int64_t row0 = t * p.tstride * BN;
       const int valid = (int)min((int64_t)BN, p.n_rows - row0);
@@ -361,10 +394,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  // pair: neither CTA may leave (or free its TMEM) while the other can still signal its barriers
+  if (NC == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (NC == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -442,7 +477,7 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, sample, qsplit, gen;
+  int bn, drift, tmax, kbs, sample, qsplit, pair, qtmem, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
@@ -450,6 +485,8 @@ struct Tunables {
     kbs = std::min(3, std::max(1, env_int("ICD_SCAN_KBS", 2)));
     sample = env_int("ICD_SCAN_SAMPLE", -1);
     qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always
+    pair = env_int("ICD_SCAN_PAIR", -1);      // CTA pairs: -1 auto (even number of query tiles >= 2), 0 off
+    qtmem = env_int("ICD_SCAN_QTMEM", 0);      // K blocks of the query tile kept in TMEM when split (0 = all that fit: 8)
     gen = 0;
   }
 };
@@ -469,6 +506,8 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(3, std::max(1, value));
   else if (!strcmp(key, "scan_sample")) t.sample = value;
   else if (!strcmp(key, "scan_qsplit")) t.qsplit = value;
+  else if (!strcmp(key, "scan_pair")) t.pair = value;
+  else if (!strcmp(key, "scan_qtmem")) t.qtmem = std::max(0, value);
   else return ICD_E_ARG;
   ++t.gen;  // tensor maps depend on bn / kbs: indexes rebuild theirs when the generation moves
   return ICD_OK;
@@ -502,6 +541,32 @@ int tensor_scan_make_map(void* map128, const void* table, int64_t n_rows, int di
                            (uint32_t)scan_bn(), (uint32_t)stage_kblocks(dim));
 }
 
+// co-resident CTA pairs the device can hold for this kernel (every CTA of a launch must be resident: the drift
+// limiter and the pruning bound make them wait on each other)
+template <int BN>
+static int resident_pairs(size_t smem) {
+  static int cached = 0;
+  if (cached) return cached;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kSMs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, scan_tc_kernel<BN, 2>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached = std::max(0, n);
+  return cached;
+}
+
 template <int BN>
 static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cudaStream_t st) {
   const int T_total = (a.B + BM - 1) / BM;
@@ -511,30 +576,53 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   // launch fills the SMs (G * T_launch <= 148) and at most tmax CTAs share one row stream
   const int n_launch = (T_total + scan_tmax() - 1) / scan_tmax();
   const int T_launch = (T_total + n_launch - 1) / n_launch;
-  int G = std::max(1, kSMs / T_launch);
+  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  // CTA pairs: every launch must hold an even number of query tiles (the pair = two neighbouring tiles)
+  bool pair = BN == 128 && tun().pair != 0 && T_launch >= 2 && T_launch % 2 == 0 && T_total % T_launch == 0;
+  int sms = kSMs;
+  if (pair) {
+    const int rp = resident_pairs<BN>((size_t)kSmemLimit);
+    if (rp * 2 < T_launch) pair = false;
+    else sms = std::min(kSMs, rp * 2);
+  }
+  const int NC = pair ? 2 : 1;
+  int G = std::max(1, sms / T_launch);
   G = (int)std::min<int64_t>(G, total_tiles);
   G = std::min(G, a.P);
   *a.groups_used = G;
 
   // Query tile placement: all of K in TMEM, or (tensor-bound launches, dim wider than 512) the K blocks that do not
-  // leave room for a second accumulator buffer in shared memory.
+  // leave room for a second accumulator buffer in shared memory (a third of K at dim = 768; the knob scan_qtmem moves
+  // more of it: measured no better, r01d pair sweep).
   const int nkb = a.dim / BK;
   const int nkb_fit2 = (kTmemCols - 2 * BN) / (BK / 2);  // K blocks that fit beside two BN-column accumulators
   const bool split = tun().qsplit > 0 || (tun().qsplit < 0 && T_launch >= 2);
-  const int nkb_tmem = (split && nkb > nkb_fit2 && BN == 128) ? nkb_fit2 : nkb;
+  int nkb_tmem = nkb;
+  if (split && nkb > nkb_fit2 && BN == 128) {
+    nkb_tmem = tun().qtmem > 0 ? std::min(tun().qtmem, nkb_fit2) : nkb_fit2;
+    nkb_tmem = std::max(nkb_tmem, nkb - 8);  // at most 8 tail tiles (128 KiB) in shared memory
+  }
   const int q_tail_tiles = nkb - nkb_tmem;
   // pipeline depth from the shared memory left after the per-thread lists
   const int kbs = stage_kblocks(a.dim);
   int nst = kMaxStages;
-  while (nst > 2 && smem_bytes(BN, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) --nst;
-  if (smem_bytes(BN, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) {
+  while (nst > 2 && smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) --nst;
+  if (smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) {
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
-  const size_t smem = smem_bytes(BN, nst, kbs, a.k, q_tail_tiles);
-  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  const size_t smem = smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles);
   CUtensorMap tmap;
-  memcpy(&tmap, map128, sizeof(CUtensorMap));
+  if (pair) {
+    // each CTA of a pair loads half of a row tile: same 3-D view of the table, box of BN / 2 rows
+    alignas(128) unsigned char pm[128];
+    ICD_TRY(make_tmap_bf16_3d(pm, a.table, BK, (uint64_t)a.n_rows, (uint64_t)(a.dim / BK), (uint64_t)a.dim * 2, BK * 2, BK,
+                              (uint32_t)(BN / 2), (uint32_t)kbs));
+    memcpy(&tmap, pm, sizeof(CUtensorMap));
+  } else {
+    memcpy(&tmap, map128, sizeof(CUtensorMap));
+  }
   int launch = 0;
   for (int qt0 = 0; qt0 < T_total; qt0 += T_launch, ++launch) {
     ScanParams p{};
@@ -560,7 +648,23 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.tstride = tstride;
     p.drift = scan_drift();
     p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64) ? a.progress + (size_t)launch * kSMs : nullptr;
-    scan_tc_kernel<BN><<<G * p.T, kThreads, smem, st>>>(tmap, p);
+    if (pair) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(G * p.T);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ICD_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<BN, 2>, tmap, p));
+    } else {
+      scan_tc_kernel<BN, 1><<<G * p.T, kThreads, smem, st>>>(tmap, p);
+    }
     count_launch();
     ICD_CUDA(cudaGetLastError());
   }

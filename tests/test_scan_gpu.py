@@ -252,3 +252,42 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         for b in range(32):
             assert ids[b, 0] == 1000 + b and ids[b, 1] == 50000 + b, (b, ids[b, :3])
     idx.close()
+
+
+@pytest.mark.parametrize("knobs", [dict(), dict(scan_tmax=2), dict(scan_qtmem=8), dict(scan_qsplit=0), dict(scan_sample=4, scan_drift=1)])
+def test_cta_pair_scan_equals_single_cta_scan(pkg, native, knobs):
+    """CTA pairs (tcgen05 cta_group::2: two query tiles per MMA, each CTA loading half of every row tile) are a
+    performance device: launches with an even number of query tiles return bit for bit what single CTAs return,
+    and both equal the oracle's exact top-k."""
+    n, B, k, dim = 70001, 512, 10, 768
+    corpus = _corpus(n, dim, seed=31)
+    corpus[2000:2032] = corpus[60000:60032]          # exact ties across row tiles and row groups
+    levels = _levels(n, seed=32)
+    q = _corpus(B, dim, seed=33)
+    q[:32] = corpus[60000:60032]
+    idx = _index(pkg, corpus, levels)
+    try:
+        native.tune(scan_pair=0)
+        s0, r0, i0 = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
+        native.tune(scan_pair=-1, **knobs)
+        s1, r1, i1 = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
+        # ragged batch: 3 query tiles + a partly filled 4th (rows of the last tile beyond B are dead lanes)
+        s2, r2, i2 = idx.search(q[:400], k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
+        # the reference's post-top-k re-rank on top of the pair scan
+        s3, r3, i3 = idx.search(q, k, weight_mode=native.WEIGHT_RERANK, path=native.PATH_TENSOR)
+    finally:
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
+    assert np.array_equal(i0, i1) and np.array_equal(r0, r1) and np.array_equal(s0, s1)
+    assert np.array_equal(i0[:400], i2) and np.array_equal(r0[:400], r2)
+    ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+    swaps = check_topk(i1, r1, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    assert swaps <= B * k // 50
+    for b in range(32):
+        assert i1[b, 0] == 2000 + b and i1[b, 1] == 60000 + b, (b, i1[b, :3])
+    # re-rank = the same k hits, re-sorted by raw * w(level) (milvus_service.py:290-314)
+    w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
+    for b in range(0, B, 37):
+        assert sorted(i3[b].tolist()) == sorted(i1[b].tolist())
+        np.testing.assert_allclose(s3[b], r3[b] * w[i3[b]], rtol=1e-6)
+        assert np.all(s3[b][:-1] >= s3[b][1:])
+    idx.close()
