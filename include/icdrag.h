@@ -168,6 +168,17 @@ int icd_encoder_forward(icd_encoder* enc, const int32_t* ids, const int32_t* len
  * fp32 [B*S, hidden] of the last forward to a host/device buffer. */
 int icd_encoder_read_hidden(icd_encoder* enc, int layer_unused, float* out, int64_t count);
 
+/* Token-classification head on the same encoder: the per-token logits that
+ * AutoModelForTokenClassification produces inside the reference's NER pipeline
+ * (services/medical_ner_service.py:76-90, called at :182).  weight [labels, hidden] and bias [labels] are
+ * classifier.weight / classifier.bias (fp32, host or device; copied).  labels <= ICD_MAX_LABELS. */
+#define ICD_MAX_LABELS 64
+int icd_encoder_set_token_head(icd_encoder* enc, const float* weight, const float* bias, int labels);
+/* logits [B, S, labels] fp32 (host or device) for ids [B, S] / lens [B] as in icd_encoder_forward; positions
+ * >= lens[b] hold the logits of padding tokens and are ignored by the caller, like the pipeline ignores them. */
+int icd_encoder_token_logits(icd_encoder* enc, const int32_t* ids, const int32_t* lens, int B, int S,
+                             float* out, void* stream, int sync);
+
 #ifdef __cplusplus
 }
 #endif

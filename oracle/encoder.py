@@ -96,8 +96,22 @@ def make_vocab(texts: Sequence[str], size: int = 21128) -> List[str]:
 
 
 def make_tokenizer(vocab_path: str):
+    """BertTokenizerFast(do_lower_case=True) over vocab.txt.  transformers >= 5 wants `vocab=` (a dict) and ignores
+    `vocab_file=`, which used to leave every character mapped to [UNK]; the size check catches that."""
     from transformers import BertTokenizerFast
-    return BertTokenizerFast(vocab_file=vocab_path, do_lower_case=True)
+    with open(vocab_path, encoding="utf-8") as fh:
+        tokens = [line.rstrip("\n") for line in fh]
+    while tokens and tokens[-1] == "":
+        tokens.pop()
+    vocab = {t: i for i, t in enumerate(tokens)}
+    for kwargs in ({"vocab": vocab}, {"vocab_file": vocab_path}):
+        try:
+            tok = BertTokenizerFast(do_lower_case=True, **kwargs)
+        except Exception:
+            continue
+        if tok.vocab_size == len(vocab):
+            return tok
+    raise RuntimeError("could not build the oracle tokenizer over " + vocab_path)
 
 
 class OracleEncoder:

@@ -32,8 +32,9 @@ SYMBOLS = [
     "icd_nccl_unique_id", "icd_shard_group_create", "icd_shard_group_destroy",
     "icd_shard_group_export_slab", "icd_shard_group_import_slabs", "icd_shard_group_search",
     "icd_encoder_weight_count", "icd_encoder_create", "icd_encoder_destroy", "icd_encoder_reserve",
-    "icd_encoder_forward", "icd_encoder_read_hidden",
+    "icd_encoder_forward", "icd_encoder_read_hidden", "icd_encoder_set_token_head", "icd_encoder_token_logits",
 ]
+MAX_LABELS = 64
 
 
 class NativeError(RuntimeError):
@@ -125,6 +126,8 @@ def _declare(L: C.CDLL) -> None:
         L.icd_encoder_reserve.argtypes = [vp, i32]
         L.icd_encoder_forward.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, i32]
         L.icd_encoder_read_hidden.argtypes = [vp, i32, vp, i64]
+        L.icd_encoder_set_token_head.argtypes = [vp, vp, vp, i32]
+        L.icd_encoder_token_logits.argtypes = [vp, vp, vp, i32, i32, vp, vp, i32]
 
 
 def check(status: int, what: str = "") -> None:

@@ -70,6 +70,9 @@ struct icd_encoder {
   void* out_stage = nullptr;
   size_t out_cap = 0;
   int last_M = 0;
+  // token-classification head (icd_encoder_set_token_head): logits = h W^T + b per token
+  float *head_w = nullptr, *head_b = nullptr;
+  int head_labels = 0;
 };
 
 namespace icd {
@@ -305,7 +308,8 @@ int icd_encoder_destroy(icd_encoder* e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   for (auto* L : e->layers) delete L;
-  void* bufs[] = {e->h, e->h1, e->t, e->ctx, e->qkv, e->f, e->ids, e->lens, e->out_stage, e->stats1, e->stats2};
+  void* bufs[] = {e->h, e->h1, e->t, e->ctx, e->qkv, e->f, e->ids, e->lens, e->out_stage, e->stats1, e->stats2,
+                  e->head_w, e->head_b};
   for (void* p : bufs)
     if (p) cudaFree(p);
   delete e;
@@ -318,19 +322,14 @@ int icd_encoder_reserve(icd_encoder* e, int max_tokens) {
   return reserve_tokens(e, max_tokens);
 }
 
-int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens, int B, int S, void* out,
-                        int out_dtype, void* stream, int sync) {
-  ICD_CHECK_ARG(e != nullptr, "encoder is null");
-  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 128, "need 1 <= S <= 128");
-  ICD_CHECK_ARG(S <= e->cfg.max_position, "S exceeds max_position");
-  const int out_flags = out_dtype;
-  out_dtype &= 0xff;
-  ICD_CHECK_ARG(out_dtype == ICD_F32 || out_dtype == ICD_BF16, "unknown out dtype");
-  if (B == 0) return ICD_OK;
-  ICD_CHECK_ARG(ids && lens && out, "null buffer");
-  ICD_CHECK_ARG((int64_t)B * S <= 0x7fffffffLL / 4, "batch too large");
-  ICD_CUDA(cudaSetDevice(e->device));
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace icd {
+
+// Runs embeddings + all layers for B sequences padded to S; on return *final_h is the [B*S, hidden] bf16 buffer of
+// last-layer hidden states and *d_lens_out the device copy of the lengths.  Work is enqueued on st.
+static int encode_hidden(icd_encoder* e, const int32_t* ids, const int32_t* lens, int B, int S, cudaStream_t st,
+                         const void** final_h_out, const int32_t** d_lens_out) {
   const int M = B * S;
   ICD_TRY(reserve_tokens(e, M));
   const int H = e->cfg.hidden, I = e->cfg.intermediate;
@@ -359,19 +358,6 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
     ICD_CUDA(cudaMemcpyAsync(e->lens, lens, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     d_lens = e->lens;
   }
-  const bool host_out = !is_device_ptr(out);
-  void* d_out = out;
-  if (host_out) {
-    const size_t need = (size_t)B * H * 4;
-    if (need > e->out_cap) {
-      if (e->out_stage) cudaFree(e->out_stage);
-      e->out_stage = nullptr;
-      ICD_CUDA(cudaMalloc(&e->out_stage, need));
-      e->out_cap = need;
-    }
-    d_out = e->out_stage;
-  }
-
   static const bool cuda_core_attention = getenv("ICD_ATTN_CUDA_CORE") != nullptr;  // A/B timing only
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
   auto attention = [&]() {
@@ -432,11 +418,101 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
       ICD_TRY(launch_layernorm(e->t, M, L->ln2g, L->ln2b, eps, e->h, st));
     }
   }
-  ICD_TRY(launch_pool_normalise(final_h, d_lens, B, S, d_out, out_flags, st));
+  *final_h_out = final_h;
+  *d_lens_out = d_lens;
   e->last_M = M;
+  return ICD_OK;
+}
+
+}  // namespace icd
+
+extern "C" {
+
+int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens, int B, int S, void* out,
+                        int out_dtype, void* stream, int sync) {
+  ICD_CHECK_ARG(e != nullptr, "encoder is null");
+  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 128, "need 1 <= S <= 128");
+  ICD_CHECK_ARG(S <= e->cfg.max_position, "S exceeds max_position");
+  const int out_flags = out_dtype;
+  out_dtype &= 0xff;
+  ICD_CHECK_ARG(out_dtype == ICD_F32 || out_dtype == ICD_BF16, "unknown out dtype");
+  if (B == 0) return ICD_OK;
+  ICD_CHECK_ARG(ids && lens && out, "null buffer");
+  ICD_CHECK_ARG((int64_t)B * S <= 0x7fffffffLL / 4, "batch too large");
+  ICD_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = e->cfg.hidden;
+  const bool host_out = !is_device_ptr(out);
+  void* d_out = out;
+  if (host_out) {
+    const size_t need = (size_t)B * H * 4;
+    if (need > e->out_cap) {
+      if (e->out_stage) cudaFree(e->out_stage);
+      e->out_stage = nullptr;
+      e->out_cap = 0;
+      ICD_CUDA(cudaMalloc(&e->out_stage, need));
+      e->out_cap = need;
+    }
+    d_out = e->out_stage;
+  }
+  const void* final_h = nullptr;
+  const int32_t* d_lens = nullptr;
+  ICD_TRY(encode_hidden(e, ids, lens, B, S, st, &final_h, &d_lens));
+  ICD_TRY(launch_pool_normalise(final_h, d_lens, B, S, d_out, out_flags, st));
   if (host_out) {
     ICD_CUDA(cudaMemcpyAsync(out, d_out, (size_t)B * H * (out_dtype == ICD_F32 ? 4 : 2), cudaMemcpyDeviceToHost, st));
   }
+  if (sync || host_out || !is_device_ptr(ids) || !is_device_ptr(lens)) ICD_CUDA(cudaStreamSynchronize(st));
+  return ICD_OK;
+}
+
+int icd_encoder_set_token_head(icd_encoder* e, const float* weight, const float* bias, int labels) {
+  ICD_CHECK_ARG(e != nullptr && weight != nullptr && bias != nullptr, "null argument");
+  ICD_CHECK_ARG(labels >= 1 && labels <= ICD_MAX_LABELS, "labels must be in [1, ICD_MAX_LABELS]");
+  ICD_CUDA(cudaSetDevice(e->device));
+  const size_t wn = (size_t)labels * e->cfg.hidden;
+  if (e->head_w) cudaFree(e->head_w);
+  if (e->head_b) cudaFree(e->head_b);
+  e->head_w = e->head_b = nullptr;
+  e->head_labels = 0;
+  ICD_CUDA(cudaMalloc((void**)&e->head_w, wn * 4));
+  ICD_CUDA(cudaMalloc((void**)&e->head_b, (size_t)labels * 4));
+  ICD_CUDA(cudaMemcpy(e->head_w, weight, wn * 4, cudaMemcpyDefault));
+  ICD_CUDA(cudaMemcpy(e->head_b, bias, (size_t)labels * 4, cudaMemcpyDefault));
+  e->head_labels = labels;
+  return ICD_OK;
+}
+
+int icd_encoder_token_logits(icd_encoder* e, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
+                             void* stream, int sync) {
+  ICD_CHECK_ARG(e != nullptr, "encoder is null");
+  ICD_CHECK_ARG(e->head_labels > 0, "no token head: call icd_encoder_set_token_head first");
+  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 128, "need 1 <= S <= 128");
+  ICD_CHECK_ARG(S <= e->cfg.max_position, "S exceeds max_position");
+  if (B == 0) return ICD_OK;
+  ICD_CHECK_ARG(ids && lens && out, "null buffer");
+  ICD_CHECK_ARG((int64_t)B * S <= 0x7fffffffLL / 4, "batch too large");
+  ICD_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = e->head_labels;
+  const size_t bytes = (size_t)B * S * L * 4;
+  const bool host_out = !is_device_ptr(out);
+  float* d_out = out;
+  if (host_out) {
+    if (bytes > e->out_cap) {
+      if (e->out_stage) cudaFree(e->out_stage);
+      e->out_stage = nullptr;
+      e->out_cap = 0;
+      ICD_CUDA(cudaMalloc(&e->out_stage, bytes));
+      e->out_cap = bytes;
+    }
+    d_out = (float*)e->out_stage;
+  }
+  const void* final_h = nullptr;
+  const int32_t* d_lens = nullptr;
+  ICD_TRY(encode_hidden(e, ids, lens, B, S, st, &final_h, &d_lens));
+  ICD_TRY(launch_token_head(final_h, B * S, e->head_w, e->head_b, L, d_out, st));
+  if (host_out) ICD_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));
   if (sync || host_out || !is_device_ptr(ids) || !is_device_ptr(lens)) ICD_CUDA(cudaStreamSynchronize(st));
   return ICD_OK;
 }

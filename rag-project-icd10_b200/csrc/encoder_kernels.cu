@@ -233,7 +233,39 @@ pool_normalise_kernel(const __nv_bfloat16* __restrict__ h, const int32_t* __rest
   }
 }
 
+// Token-classification head (BertForTokenClassification.classifier): one warp per token row.  The row (768 bf16)
+// sits in registers, 24 elements per lane; the L weight rows stream from L1/L2 (the same 3 KiB rows for every
+// warp) as coalesced fp32 and each label costs one warp reduction.  HBM-bound on the hidden states (1.5 KB per
+// token in, 4 L bytes out).
+__global__ void __launch_bounds__(256)
+token_head_kernel(const __nv_bfloat16* __restrict__ h, int M, const float* __restrict__ w,
+                  const float* __restrict__ b, int L, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float x[24];
+  const __nv_bfloat16* row = h + (size_t)m * H;
+#pragma unroll
+  for (int j = 0; j < 24; ++j) x[j] = __bfloat162float(row[j * 32 + lane]);
+  for (int l = 0; l < L; ++l) {
+    const float* wr = w + (size_t)l * H;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) acc = fmaf(x[j], __ldg(wr + j * 32 + lane), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)m * L + l] = acc + __ldg(b + l);
+  }
+}
+
 }  // namespace
+
+int launch_token_head(const void* h, int M, const float* w, const float* b, int L, float* out, cudaStream_t st) {
+  if (M <= 0) return ICD_OK;
+  token_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h), M, w, b, L, out);
+  count_launch();
+  ICD_CUDA(cudaGetLastError());
+  return ICD_OK;
+}
 
 int launch_embed_ln(const int32_t* ids, int M, int S, const float* word, const float* pos, const float* type0,
                     const float* gamma, const float* beta, float eps, void* out, cudaStream_t st) {

@@ -48,4 +48,7 @@ int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S,
 int launch_pool_normalise(const void* h_bf16, const int32_t* lens, int B, int S, void* out, int out_dtype,
                           cudaStream_t st);
 
+// logits[m, l] = h[m, :] . w[l, :] + b[l]  (h bf16 [M, 768], w fp32 [L, 768], out fp32 [M, L]); L <= 64
+int launch_token_head(const void* h_bf16, int M, const float* w, const float* b, int L, float* out, cudaStream_t st);
+
 }  // namespace icd

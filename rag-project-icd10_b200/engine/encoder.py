@@ -104,6 +104,32 @@ class EncoderEngine:
                                             C.c_void_p(stream), 1 if sync else 0), "icd_encoder_forward")
         return out
 
+    def set_token_head(self, weight: np.ndarray, bias: np.ndarray) -> None:
+        """classifier.weight [labels, hidden] / classifier.bias [labels] of a BertForTokenClassification."""
+        weight = np.ascontiguousarray(weight, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        if weight.ndim != 2 or weight.shape[1] != self.cfg.hidden or bias.shape != (weight.shape[0],):
+            raise ValueError("token head must be weight [labels, hidden] and bias [labels]")
+        N.check(N.lib().icd_encoder_set_token_head(self._h, N.buf_ptr(weight), N.buf_ptr(bias), int(weight.shape[0])),
+                "icd_encoder_set_token_head")
+        self.num_labels = int(weight.shape[0])
+
+    def token_logits(self, ids, lens, out=None, stream: int = 0, sync: bool = True):
+        """ids [B,S] int32, lens [B] int32 -> per-token logits [B,S,labels] float32 (set_token_head first)."""
+        B, S = int(ids.shape[0]), int(ids.shape[1])
+        L = getattr(self, "num_labels", 0)
+        if L <= 0:
+            raise N.NativeError("no token head set on this encoder")
+        if out is None:
+            if N._is_torch(ids) and ids.is_cuda:
+                import torch
+                out = torch.empty((B, S, L), dtype=torch.float32, device=ids.device)
+            else:
+                out = np.empty((B, S, L), np.float32)
+        N.check(N.lib().icd_encoder_token_logits(self._h, N.buf_ptr(ids), N.buf_ptr(lens), B, S, N.buf_ptr(out),
+                                                 C.c_void_p(stream), 1 if sync else 0), "icd_encoder_token_logits")
+        return out
+
     def read_hidden(self, tokens: int) -> np.ndarray:
         out = np.empty((tokens, self.cfg.hidden), np.float32)
         N.check(N.lib().icd_encoder_read_hidden(self._h, 0, N.buf_ptr(out), out.size), "icd_encoder_read_hidden")
@@ -123,15 +149,42 @@ def _device_index(device) -> int:
     raise N.NativeError(f"EncoderEngine runs on CUDA devices only (got device={device!r}); there is no CPU fallback")
 
 
+def bert_tokenizer_from_vocab(vocab_path: str, do_lower_case: bool = True):
+    """BertTokenizerFast over a vocab.txt.  transformers >= 5 takes the vocabulary as `vocab=` (a token -> id dict)
+    and silently ignores `vocab_file=` (leaving a 5-token vocabulary that maps every character to [UNK]);
+    transformers 4 takes `vocab_file=`.  Either way the result is checked against the file."""
+    from transformers import BertTokenizerFast
+    with open(vocab_path, encoding="utf-8") as fh:
+        tokens = [line.rstrip("\n") for line in fh]
+    while tokens and tokens[-1] == "":
+        tokens.pop()
+    vocab = {t: i for i, t in enumerate(tokens)}
+    tok = None
+    for kwargs in ({"vocab": vocab}, {"vocab_file": vocab_path}):
+        try:
+            cand = BertTokenizerFast(do_lower_case=do_lower_case, **kwargs)
+        except Exception:
+            continue
+        if cand.vocab_size == len(vocab):
+            tok = cand
+            break
+    if tok is None:
+        raise RuntimeError(f"could not build a BERT tokenizer over {vocab_path} ({len(vocab)} entries)")
+    return tok
+
+
 def load_tokenizer(path: str):
     """The model directory's own tokenizer; falls back to BertTokenizerFast over vocab.txt."""
-    from transformers import AutoTokenizer, BertTokenizerFast
+    from transformers import AutoTokenizer
+    vocab_path = os.path.join(path, "vocab.txt")
     try:
         if os.path.exists(os.path.join(path, "tokenizer_config.json")) or os.path.exists(os.path.join(path, "tokenizer.json")):
-            return AutoTokenizer.from_pretrained(path, local_files_only=True)
+            tok = AutoTokenizer.from_pretrained(path, local_files_only=True)
+            if tok.vocab_size > 5 or not os.path.exists(vocab_path):   # a 5-token vocabulary = the file was ignored
+                return tok
     except Exception:
         pass
-    return BertTokenizerFast(vocab_file=os.path.join(path, "vocab.txt"), do_lower_case=True)
+    return bert_tokenizer_from_vocab(vocab_path)
 
 
 # ------------------------------------------------------------------------------------------

@@ -75,17 +75,22 @@ def resolve_model_dir(name_or_path: str) -> str:
             f"(set ICD_B200_MODEL_DIR to a directory with config.json, model.safetensors, vocab.txt)") from e
 
 
+def load_state(path: str) -> dict:
+    """name -> tensor of an HF model directory (model.safetensors, else pytorch_model.bin)."""
+    st = os.path.join(path, "model.safetensors")
+    if os.path.exists(st):
+        from safetensors.numpy import load_file
+        return load_file(st)
+    import torch
+    state = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    return {k: v.float().numpy() for k, v in state.items()}
+
+
 def load_model_dir(path: str) -> Tuple[N.BertCfg, np.ndarray, dict]:
     with open(os.path.join(path, "config.json"), encoding="utf-8") as fh:
         cfg_d = json.load(fh)
     cfg = config_from_dict(cfg_d)
-    st = os.path.join(path, "model.safetensors")
-    if os.path.exists(st):
-        from safetensors.numpy import load_file
-        state = load_file(st)
-    else:
-        import torch
-        state = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+    state = load_state(path)
     meta = {"max_seq_length": 128, "do_lower_case_text": False}
     sb = os.path.join(path, "sentence_bert_config.json")
     if os.path.exists(sb):

@@ -122,3 +122,23 @@ def test_embedding_service_text_rules_and_errors():
         assert es.get_model_info() == {"loaded": False}
     finally:
         E.EmbeddingService.engine_factory = old
+
+
+def test_tokenizers_read_the_vocab_file(tmp_path):
+    """transformers >= 5 ignores BertTokenizerFast(vocab_file=...) and falls back to a 5-token vocabulary, which turns
+    every character into [UNK]: both the oracle's and the product's tokenizer must really use vocab.txt (ids of
+    bert-base-chinese specials, no [UNK] for characters the vocabulary holds) and agree with each other."""
+    import importlib
+    from oracle import encoder as oenc
+    texts = ["query: 霍乱 | 未特指的霍乱 | ICD-10: A00.901", "急性胃肠炎 发热"]
+    vocab = oenc.make_vocab(texts, size=3000)
+    p = tmp_path / "vocab.txt"
+    p.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    a = oenc.make_tokenizer(str(p))
+    b = importlib.import_module("rag-project-icd10_b200.engine.encoder").load_tokenizer(str(tmp_path))
+    for tok in (a, b):
+        assert tok.vocab_size == 3000
+        assert (tok.pad_token_id, tok.unk_token_id, tok.cls_token_id, tok.sep_token_id) == (0, 100, 101, 102)
+        ids = tok(texts[1])["input_ids"]
+        assert ids[0] == 101 and ids[-1] == 102 and 100 not in ids and len(set(ids)) >= 8
+    assert a(texts)["input_ids"] == b(texts)["input_ids"]
