@@ -4,10 +4,11 @@
 //
 // Replaces the nn.Linear calls inside SentenceTransformer.encode (reference call sites
 // services/embedding_service.py:81,97-102,120): QKV projection, attention output projection,
-// FFN up (+ erf-GELU) and FFN down (+ residual).  One persistent CTA per SM walks 128 x 256
-// output tiles; A and W tiles arrive through TMA (128-byte swizzle) into a 4-stage mbarrier
-// ring; tcgen05.mma (M=128, N=256, K=16) accumulates in TMEM, double-buffered (2 x 256
-// columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// FFN up (+ erf-GELU) and FFN down (+ residual).  Persistent kernel: one CTA PAIR per TPC (cluster of 2,
+// tcgen05 cta_group::2) walks 256 x 256 output tiles -- each CTA loads its own 128 rows of A and half of the W
+// tile through TMA (128-byte swizzle) into a 5-stage mbarrier ring, the leader issues tcgen05.mma
+// (M=256, N=256, K=16), the accumulators sit in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  (NC = 1: single CTAs on 128 x 256 tiles, the A/B reference and the fallback.)
 //
 // Epilogue: thread == TMEM lane == output row, so a direct global store would scatter 16-byte
 // pieces over 32 rows per instruction (ncu r01b: the K=768 GEMMs were bound by exactly that:

@@ -94,3 +94,38 @@ def bootstrap_exchange(dist, rank: int, world: int, ident, handle, share_ident: 
 def shard_bounds(total_rows: int, rank: int, world: int):
     """Rows [lo, hi) of rank r: contiguous, sizes differ by at most one."""
     return total_rows * rank // world, total_rows * (rank + 1) // world
+
+
+# ------------------------------------------------------------------ data-parallel encoder (SURVEY 8e, encoder row)
+def partition_by_tokens(token_counts, world: int):
+    """Splits sentence indices over `world` ranks with (nearly) equal TOKEN totals: longest-first onto the
+    least-loaded rank.  Replicas share no state, so balance is the only thing that matters; each rank then
+    length-buckets its own share (EncoderEngine._encode_ids).  Returns a list of index lists, each ascending."""
+    order = sorted(range(len(token_counts)), key=lambda j: (-int(token_counts[j]), j))
+    loads = [0] * world
+    parts = [[] for _ in range(world)]
+    for j in order:
+        r = min(range(world), key=lambda x: (loads[x], x))
+        parts[r].append(j)
+        loads[r] += int(token_counts[j])
+    return [sorted(p) for p in parts]
+
+
+def encode_data_parallel(encode_fn, texts, token_counts, rank: int, world: int, dist=None, dim: int = 768):
+    """Every rank encodes its share of `texts` with its own encoder replica (`encode_fn(list[str]) -> [m, dim]
+    float32 array`); no collective on the data path.  With `dist` (torch.distributed, any backend) the shares are
+    all-gathered so every rank returns the full [n, dim] matrix in input order; without it only this rank's rows
+    are filled (the build tool's case: shard r encodes exactly the rows it will hold)."""
+    parts = partition_by_tokens(token_counts, world)
+    mine = parts[rank]
+    out = np.zeros((len(texts), dim), np.float32)
+    local = np.asarray(encode_fn([texts[j] for j in mine]), np.float32).reshape(len(mine), dim) if mine else \
+        np.zeros((0, dim), np.float32)
+    out[mine] = local
+    if dist is not None and world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        for r in range(world):
+            if parts[r]:
+                out[parts[r]] = gathered[r]
+    return out

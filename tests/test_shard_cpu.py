@@ -80,3 +80,50 @@ def test_bootstrap_exchange_gloo_world2():
         p.join(timeout=60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def test_partition_by_tokens_balances_and_covers():
+    shard = importlib.import_module("rag-project-icd10_b200.engine.shard")
+    rng = np.random.default_rng(3)
+    counts = rng.integers(3, 129, size=1001).tolist()
+    for world in (1, 2, 3, 8):
+        parts = shard.partition_by_tokens(counts, world)
+        assert sorted(j for p in parts for j in p) == list(range(len(counts)))
+        loads = [sum(counts[j] for j in p) for p in parts]
+        assert max(loads) - min(loads) <= 128          # within one longest sentence
+    assert shard.partition_by_tokens([], 4) == [[], [], [], []]
+    assert shard.partition_by_tokens([5], 2) == [[0], []]
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shard = importlib.import_module("rag-project-icd10_b200.engine.shard")
+    texts = ["t%03d" % i + "x" * (i % 17) for i in range(53)]
+    counts = [len(t) + 2 for t in texts]
+
+    def fake_encode(batch):           # a deterministic stand-in for an encoder replica
+        return np.stack([np.full(8, float(int(t[1:4])), np.float32) for t in batch]) if batch else np.zeros((0, 8), np.float32)
+    full = shard.encode_data_parallel(fake_encode, texts, counts, rank, world, dist=dist, dim=8)
+    local = shard.encode_data_parallel(fake_encode, texts, counts, rank, world, dist=None, dim=8)
+    mine = shard.partition_by_tokens(counts, world)[rank]
+    ok_full = bool(np.array_equal(full[:, 0], np.arange(53, dtype=np.float32)))
+    ok_local = bool(np.array_equal(local[mine, 0], np.asarray(mine, np.float32))) and float(np.abs(local).sum()) == float(sum(mine)) * 8
+    q.put((rank, ok_full, ok_local))
+    dist.destroy_process_group()
+
+
+def test_encode_data_parallel_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res), res
