@@ -481,7 +481,7 @@ struct Tunables {
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
-    tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 8)));
+    tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 16)));
     kbs = std::min(3, std::max(1, env_int("ICD_SCAN_KBS", 2)));
     sample = env_int("ICD_SCAN_SAMPLE", -1);
     qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always

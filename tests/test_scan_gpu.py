@@ -234,7 +234,7 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         native.tune(**knobs)
         score, raw, ids = idx.search(q, k, weight_mode=weight_mode, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2, scan_qsplit=-1)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=2, scan_qsplit=-1)
     if weight_mode == native.WEIGHT_PRE:
         w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
         full = (q @ corpus.T) * w[None, :]
@@ -276,7 +276,7 @@ def test_cta_pair_scan_equals_single_cta_scan(pkg, native, knobs):
         # the reference's post-top-k re-rank on top of the pair scan
         s3, r3, i3 = idx.search(q, k, weight_mode=native.WEIGHT_RERANK, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=8, scan_kbs=2, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=2, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
     assert np.array_equal(i0, i1) and np.array_equal(r0, r1) and np.array_equal(s0, s1)
     assert np.array_equal(i0[:400], i2) and np.array_equal(r0[:400], r2)
     ref_s, ref_i = osearch.exact_topk(corpus, q, k)
