@@ -101,6 +101,43 @@ def test_device_tensors_and_large_batch(small):
     assert cosine_rows(out.cpu().numpy(), ref).min() >= COS_MIN
 
 
+def test_deferred_layernorm_with_shifted_and_scaled_streams():
+    """The LayerNorms are folded into the GEMMs on either side of them (csrc/gemm_tc.cu: y = rs (x W'^T) - rs mu c + b').
+    That identity cancels mu c against the accumulator, so it is exercised where it is least comfortable: residual
+    streams whose per-row mean is several standard deviations from zero (large output biases) and LayerNorm gains /
+    offsets far from (1, 0)."""
+    import torch
+    N, E, W = _mods()
+    vocab, layers = 1500, 3
+    state = oenc.synthetic_state_dict(seed=21, num_layers=layers, vocab_size=vocab)
+    g = torch.Generator().manual_seed(99)
+    for name in list(state):
+        if name.endswith("attention.output.dense.bias") or name.endswith("output.dense.bias"):
+            state[name] = state[name] + 3.0                       # row mean ~ +3 sigma of the sublayer output
+        elif name.endswith("LayerNorm.weight"):
+            state[name] = 0.25 + 2.0 * torch.rand(state[name].shape, generator=g)
+        elif name.endswith("LayerNorm.bias"):
+            state[name] = 1.5 * torch.randn(state[name].shape, generator=g)
+    cfg = N.BertCfg(vocab_size=vocab, hidden=768, layers=layers, heads=12, intermediate=3072, max_position=512,
+                    type_vocab=2, ln_eps=1e-12)
+    eng = E.EncoderEngine(cfg=cfg, blob=W.pack_state_dict(state, cfg), tokenizer=object(), device=0, max_tokens=8192)
+    try:
+        rng = np.random.default_rng(8)
+        B, S = 70, 48
+        lens = rng.integers(1, S + 1, size=B).astype(np.int32)
+        ids = np.zeros((B, S), np.int32)
+        for b in range(B):
+            ids[b, :lens[b]] = rng.integers(1, vocab, size=lens[b])
+        got = eng.forward_ids(ids, lens)
+        ref, _, ref_h = _oracle_forward(state, layers, vocab, ids, lens)
+        assert cosine_rows(got, ref).min() >= COS_MIN
+        hid = eng.read_hidden(B * S).reshape(B, S, 768)
+        for b in range(0, B, 7):
+            assert cosine_rows(hid[b, :lens[b]], ref_h[b, :lens[b]]).min() >= 0.998
+    finally:
+        eng.close()
+
+
 @pytest.fixture(scope="module")
 def full12(tmp_path_factory):
     """12-layer synthetic model + synthetic vocab over the real ICD texts, saved as an HF dir."""
