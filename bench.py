@@ -448,6 +448,9 @@ def main():
                         "tflops": world * enc["flops_per_batch"] / (ms * 1e-3) / 1e12,
                         "frac_of_bf16_sustained": enc["flops_per_batch"] / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
                         "scaling": "weak (one batch per GPU, replicas, no collective)"})
+            if "roofline" in enc:   # per-GPU figure from the max-over-ranks time, like frac_of_bf16_sustained
+                enc["roofline"]["achieved"] = enc["flops_per_batch"] / (ms * 1e-3) / 1e12
+                enc["roofline"]["frac"] = enc["roofline"]["achieved"] / enc["roofline"]["peak"]
 
     if rank == 0:
         flops = 2.0 * B * rows_local * DIM                     # per scan launch (per GPU)
