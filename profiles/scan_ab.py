@@ -10,7 +10,7 @@ VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").Vec
 rows, B, k = int(os.environ.get("ROWS", 100_000_000)), int(os.environ.get("BATCH", 1024)), 10
 steps = int(os.environ.get("STEPS", 5))
 variants = [v for v in os.environ.get("VARIANTS", "scan_pair=-1;scan_pair=0").split(";") if v]
-DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=2, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
+DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
 dev = torch.device("cuda", 0)
 table, levels = bench.make_corpus(torch, rows, dev, 1234)
 q = bench.make_queries(torch, B, dev)

@@ -477,12 +477,13 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, sample, qsplit, pair, qtmem, gen;
+  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
     tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 16)));
-    kbs = std::min(3, std::max(1, env_int("ICD_SCAN_KBS", 2)));
+    kbs = std::min(6, std::max(1, env_int("ICD_SCAN_KBS", 3)));            // K blocks per stage, single CTAs
+    kbs_pair = std::min(6, std::max(1, env_int("ICD_SCAN_KBS_PAIR", 6)));  // ... CTA pairs (half-height boxes)
     sample = env_int("ICD_SCAN_SAMPLE", -1);
     qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always
     pair = env_int("ICD_SCAN_PAIR", -1);      // CTA pairs: -1 auto (even number of query tiles >= 2), 0 off
@@ -503,7 +504,8 @@ int tensor_scan_tune(const char* key, int value) {
   if (!strcmp(key, "scan_bn")) t.bn = value == 64 ? 64 : 128;
   else if (!strcmp(key, "scan_drift")) t.drift = std::max(0, value);
   else if (!strcmp(key, "scan_tmax")) t.tmax = std::min(32, std::max(1, value));
-  else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(3, std::max(1, value));
+  else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(6, std::max(1, value));
+  else if (!strcmp(key, "scan_kbs_pair")) t.kbs_pair = std::min(6, std::max(1, value));
   else if (!strcmp(key, "scan_sample")) t.sample = value;
   else if (!strcmp(key, "scan_qsplit")) t.qsplit = value;
   else if (!strcmp(key, "scan_pair")) t.pair = value;
@@ -597,31 +599,47 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   // more of it: measured no better, r01d pair sweep).
   const int nkb = a.dim / BK;
   const int nkb_fit2 = (kTmemCols - 2 * BN) / (BK / 2);  // K blocks that fit beside two BN-column accumulators
-  const bool split = tun().qsplit > 0 || (tun().qsplit < 0 && T_launch >= 2);
-  int nkb_tmem = nkb;
-  if (split && nkb > nkb_fit2 && BN == 128) {
-    nkb_tmem = tun().qtmem > 0 ? std::min(tun().qtmem, nkb_fit2) : nkb_fit2;
-    nkb_tmem = std::max(nkb_tmem, nkb - 8);  // at most 8 tail tiles (128 KiB) in shared memory
+  // the split pays at every batch size (r01e: B = 8 0.94 -> 1.02, B = 32 0.93 -> 0.97, B = 128 0.885 -> 0.92 of the
+  // HBM peak: the drain no longer holds up the next tile's MMAs); it is dropped when the candidate lists (large k)
+  // leave fewer than three pipeline stages beside the 64 KiB tail
+  const bool want_split = tun().qsplit != 0 && nkb > nkb_fit2 && BN == 128;
+  // K blocks per stage: longer K slices per bulk copy are longer DRAM bursts and fewer barrier round trips per
+  // tile (r01e, 10 M rows, pairs, B = 1024: 2 -> 0.82, 3 -> 0.88, 4 -> 0.91, 6 -> 0.94 of sustained bf16 peak; single
+  // CTAs at B = 128 peak at 3).  Largest divisor of nkb <= the knob that still leaves >= 3 stages beside the Q tail;
+  // if none does, the split goes first, then the stage shrinks.
+  const int kbs_want = std::min(pair ? tun().kbs_pair : tun().kbs, nkb);
+  int kbs = 0, nkb_tmem = nkb, q_tail_tiles = 0, nst = 0;
+  for (int pass = 0; pass < 2 && kbs == 0; ++pass) {
+    const bool split = pass == 0 && want_split;
+    if (pass == 0 && !want_split) continue;
+    int tmem_kb = nkb;
+    if (split) {
+      tmem_kb = tun().qtmem > 0 ? std::min(tun().qtmem, nkb_fit2) : nkb_fit2;
+      tmem_kb = std::max(tmem_kb, nkb - 8);  // at most 8 tail tiles (128 KiB) in shared memory
+    }
+    for (int c = kbs_want; c >= 1 && kbs == 0; --c) {
+      if (nkb % c) continue;
+      int n = kMaxStages;
+      while (n > 2 && smem_bytes(BN / NC, n, c, a.k, nkb - tmem_kb) > (size_t)kSmemLimit) --n;
+      if (smem_bytes(BN / NC, n, c, a.k, nkb - tmem_kb) > (size_t)kSmemLimit) continue;
+      if (split && n < 3) continue;
+      kbs = c, nst = n, nkb_tmem = tmem_kb, q_tail_tiles = nkb - tmem_kb;
+    }
   }
-  const int q_tail_tiles = nkb - nkb_tmem;
-  // pipeline depth from the shared memory left after the per-thread lists
-  const int kbs = stage_kblocks(a.dim);
-  int nst = kMaxStages;
-  while (nst > 2 && smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) --nst;
-  if (smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles) > (size_t)kSmemLimit) {
+  if (kbs == 0) {
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
   const size_t smem = smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles);
+  // the stage shape is chosen per launch, so the 3-D view {64 elements, rows, K blocks} of the table is encoded here
+  // (a host-side call of a few microseconds); each CTA of a pair loads half of a row tile
+  (void)map128;
   CUtensorMap tmap;
-  if (pair) {
-    // each CTA of a pair loads half of a row tile: same 3-D view of the table, box of BN / 2 rows
+  {
     alignas(128) unsigned char pm[128];
     ICD_TRY(make_tmap_bf16_3d(pm, a.table, BK, (uint64_t)a.n_rows, (uint64_t)(a.dim / BK), (uint64_t)a.dim * 2, BK * 2, BK,
-                              (uint32_t)(BN / 2), (uint32_t)kbs));
+                              (uint32_t)(BN / NC), (uint32_t)kbs));
     memcpy(&tmap, pm, sizeof(CUtensorMap));
-  } else {
-    memcpy(&tmap, map128, sizeof(CUtensorMap));
   }
   int launch = 0;
   for (int qt0 = 0; qt0 < T_total; qt0 += T_launch, ++launch) {

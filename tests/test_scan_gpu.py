@@ -213,7 +213,7 @@ def test_full_size_properties(pkg, native):
 
 
 @pytest.mark.parametrize("knobs", [dict(scan_sample=4), dict(scan_sample=3, scan_drift=1), dict(scan_sample=0, scan_drift=0),
-                                   dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=3),
+                                   dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=2), dict(scan_kbs=6), dict(scan_kbs=4, scan_qsplit=0),
                                    dict(scan_qsplit=0), dict(scan_qsplit=1, scan_sample=4), dict(scan_qsplit=1, scan_tmax=1)])
 @pytest.mark.parametrize("weight_mode", [2, 1])
 def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
@@ -234,7 +234,7 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         native.tune(**knobs)
         score, raw, ids = idx.search(q, k, weight_mode=weight_mode, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=2, scan_qsplit=-1)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_qsplit=-1)
     if weight_mode == native.WEIGHT_PRE:
         w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
         full = (q @ corpus.T) * w[None, :]
@@ -254,7 +254,8 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
     idx.close()
 
 
-@pytest.mark.parametrize("knobs", [dict(), dict(scan_tmax=2), dict(scan_qtmem=8), dict(scan_qsplit=0), dict(scan_sample=4, scan_drift=1)])
+@pytest.mark.parametrize("knobs", [dict(), dict(scan_tmax=2), dict(scan_qtmem=8), dict(scan_qsplit=0), dict(scan_sample=4, scan_drift=1),
+                                   dict(scan_kbs_pair=2), dict(scan_kbs_pair=4, scan_qsplit=0), dict(scan_kbs_pair=3)])
 def test_cta_pair_scan_equals_single_cta_scan(pkg, native, knobs):
     """CTA pairs (tcgen05 cta_group::2: two query tiles per MMA, each CTA loading half of every row tile) are a
     performance device: launches with an even number of query tiles return bit for bit what single CTAs return,
@@ -276,7 +277,7 @@ def test_cta_pair_scan_equals_single_cta_scan(pkg, native, knobs):
         # the reference's post-top-k re-rank on top of the pair scan
         s3, r3, i3 = idx.search(q, k, weight_mode=native.WEIGHT_RERANK, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=2, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_kbs_pair=6, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
     assert np.array_equal(i0, i1) and np.array_equal(r0, r1) and np.array_equal(s0, s1)
     assert np.array_equal(i0[:400], i2) and np.array_equal(r0[:400], r2)
     ref_s, ref_i = osearch.exact_topk(corpus, q, k)
