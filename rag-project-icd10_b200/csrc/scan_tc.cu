@@ -9,8 +9,9 @@
 //     shared memory is free for streaming the table.
 //   * table rows stream HBM -> shared memory through TMA in a ring of mbarrier-tracked stages
 //     and are the MMA B operand (K-major).  The table is described to TMA as a 3-D tensor
-//     {64 elements, rows, K blocks} so ONE bulk copy brings a whole stage -- 64 rows x (kbs x 64)
-//     bf16, laid out as kbs consecutive 128 x 64 tiles in the 128-byte-swizzle canonical layout.
+//     {64 elements, rows, K blocks} so ONE bulk copy brings a whole stage -- 128 (pairs: 64) rows x (kbs x 64)
+//     bf16, laid out as kbs consecutive row-tile x 64 tiles in the 128-byte-swizzle canonical layout.  kbs is
+//     chosen per launch (up to 6 = 768-byte bursts per row for pairs, 3 for single CTAs: launch_tensor_scan_bn).
 //   * tcgen05.mma (M=128 queries, N=128 rows, K=16) accumulates a 128x128 fp32 tile in TMEM.
 //     N must be >= 128: with A in TMEM every MMA re-reads the 128x16 A slice (4 KiB) at the
 //     TMEM read rate, ~64 cycles, so N=64 (32 cycles of math) runs the pipe at half rate
