@@ -309,6 +309,70 @@ class HierarchicalSimilarityService:
         logger.info(f"批量相似度计算完成，平均增强分数: {float(np.mean([t[1] for t in out])):.4f}")
         return out
 
+    # ------------------------------------------------------------------ many candidate lists at once
+    def weighted_scores(self, F: np.ndarray) -> np.ndarray:
+        """_calculate_weighted_score over a [P, 6] float64 array of factors (columns in SimilarityFactors order), one
+        vectorised pass; the operation order per element is the scalar function's, so results are bit-identical."""
+        w, n = self.factor_weights, _NORMALISERS
+        base, hb, em, sc, ca, cr = (F[:, i] for i in range(6))
+        precise = base > 0.95
+        extra = np.zeros_like(base)
+        extra = extra + hb * w["hierarchy_boost"] / n["hierarchy_boost"] * np.where(precise, 0.5, 1.0)
+        extra = extra + em * w["entity_match_score"] / n["entity_match_score"]
+        extra = extra + np.where(sc > base, (sc - base) * w["semantic_coherence"] / n["semantic_coherence"], 0.0)
+        extra = extra + ca * w["category_alignment"] / n["category_alignment"]
+        extra = extra + cr * w["context_relevance"] / n["context_relevance"]
+        extra = extra + np.where(precise, 0.15, 0.0)
+        return np.minimum(base + extra, 1.8)
+
+    def batch_calculate_similarities_many(self, requests):
+        """All diagnoses of a request in one call: `requests` is a list of (query_text, query_entities,
+        candidate_records) -- e.g. one entry per extracted diagnosis with the rows MilvusService.search_batch
+        returned for it.  The string-dependent factors are computed per (query, candidate) on the host exactly as
+        in batch_calculate_similarities; the weighted score of ALL pairs is then one vectorised pass
+        (weighted_scores).  Returns one list per request, identical -- records, scores, factors, order -- to
+        calling batch_calculate_similarities(query_text, query_entities, candidate_records) on each."""
+        plans, rows = [], []          # rows: (request index, record, factors | None, exact)
+        for ri, (query_text, query_entities, candidate_records) in enumerate(requests):
+            core, candidates = self.uncertainty_service.process_uncertainty_query(query_text, candidate_records)
+            plans.append(len(candidates))
+            for rec in candidates:
+                factors = SimilarityFactors()
+                try:
+                    exact = rec.get("preferred_zh", "").strip() == core.strip()
+                    factors.vector_similarity = self._calculate_vector_similarity(core, rec)
+                    if exact and factors.vector_similarity < 0.9:
+                        factors.vector_similarity = 1.0
+                    factors.hierarchy_boost = self._calculate_hierarchy_boost(core, query_entities, rec)
+                    factors.entity_match_score = self._calculate_entity_match_score(query_entities, rec)
+                    factors.semantic_coherence = self._calculate_semantic_coherence(core, rec)
+                    factors.category_alignment = self._calculate_category_alignment(query_entities, rec)
+                    factors.context_relevance = self._calculate_context_relevance(core, rec)
+                    rows.append((ri, rec, factors, exact, True))
+                except Exception as e:   # the scalar path's degrade contract: the candidate keeps its own score
+                    logger.error(f"增强相似度计算失败: {e}")
+                    rows.append((ri, rec, factors, False, False))
+        F = np.array([[getattr(f, fld.name) for fld in fields(SimilarityFactors)] for _, _, f, _, _ in rows],
+                     dtype=np.float64).reshape(len(rows), 6)
+        totals = self.weighted_scores(F) if len(rows) else np.zeros(0)
+        out = [[] for _ in requests]
+        for (ri, rec, factors, exact, ok), total in zip(rows, totals):
+            if ok:
+                score = float(max(float(total), 1.5)) if exact else float(total)
+            else:
+                score = float(rec.get("score", 0.0))
+            item = rec.copy()
+            item["enhanced_score"] = score
+            item["original_score"] = rec.get("original_score", rec.get("score", 0.0))
+            item["similarity_factors"] = factors
+            if "uncertainty_boost" in rec:
+                item["uncertainty_boost"] = rec["uncertainty_boost"]
+                item["uncertainty_weight"] = rec["uncertainty_weight"]
+            out[ri].append((item, score, factors))
+        for lst in out:
+            lst.sort(key=lambda t: t[1], reverse=True)
+        return out
+
     # reference :581-624
     def get_similarity_explanation(self, factors: SimilarityFactors) -> Dict[str, Any]:
         detail = {}

@@ -78,3 +78,29 @@ def test_update_weights_normalises():
     svc = H.HierarchicalSimilarityService(None)
     svc.update_weights({"vector_similarity": 1.0, "nope": 3.0})
     assert abs(sum(svc.factor_weights.values()) - 1.0) < 1e-12 and "nope" not in svc.factor_weights
+
+
+def test_many_lists_at_once_equals_one_list_at_a_time():
+    """the vectorised weighted score over all (diagnosis, candidate) pairs of a request returns
+    exactly what batch_calculate_similarities returns per diagnosis (records, scores, factors, order) -- and hence
+    the reference's golden outputs."""
+    g = _golden()
+    H = importlib.import_module("rag-project-icd10_b200.services.hierarchical_similarity_service")
+    for service in ("plain", "with_embedding"):
+        svc = H.HierarchicalSimilarityService(_GoldenEmbedding() if service == "with_embedding" else None)
+        cases = [c for c in g["cases"] if (c["service"] == "with_embedding") == (service == "with_embedding")]
+        reqs = [(c["query"], g["entities"] if c["entities"] == "ents" else {},
+                 [dict(r) for r in (g["flat"] if c["candidates"] == "flat" else g["nested"])]) for c in cases]
+        many = svc.batch_calculate_similarities_many(reqs)
+        assert len(many) == len(reqs)
+        for (q, ents, cands), got in zip(reqs, many):
+            one = svc.batch_calculate_similarities(q, ents, [dict(r) for r in cands])
+            assert len(got) == len(one)
+            for (ra, sa, fa), (rb, sb, fb) in zip(got, one):
+                assert sa == sb and fa == fb and ra.get("code") == rb.get("code")
+                assert _jsonable({k: v for k, v in ra.items() if k != "similarity_factors"}) == \
+                       _jsonable({k: v for k, v in rb.items() if k != "similarity_factors"})
+    assert svc.batch_calculate_similarities_many([]) == []
+    F = np.array([[0.97, 0.3, 0.1, 0.99, 0.2, 0.1], [0.5, 0.0, 0.0, 0.3, 0.0, 0.0], [1.0, 1.0, 1.0, 1.0, 1.0, 1.0]])
+    scalar = [svc._calculate_weighted_score(H.SimilarityFactors(*row)) for row in F]
+    assert svc.weighted_scores(F).tolist() == scalar
