@@ -69,3 +69,35 @@ def test_softmax_and_tag_rules():
     assert np.isfinite(p).all() and p[0].argmax() == 2
     assert TC._get_tag("B-Symptom") == ("B", "Symptom") and TC._get_tag("I-Drug") == ("I", "Drug")
     assert TC._get_tag("O") == ("I", "O")
+
+
+def test_grouping_rules_match_pipeline_on_crafted_label_sequences(tiny):
+    """B-/I- boundary rules of the "simple" strategy on hand-made label sequences (two B- in a row stay apart, an I-
+    of another type starts a new group, O runs are dropped, [UNK] takes its word from the text), fed through the
+    transformers pipeline's own aggregate() and through the restatement."""
+    from transformers.pipelines.token_classification import AggregationStrategy
+    model, tok = tiny
+    TC = importlib.import_module("rag-project-icd10_b200.engine.token_classifier")
+    pipe = nc.hf_pipeline(model, tok)
+    id2label = dict(enumerate(nc.LABELS))
+    text = "急性胃肠炎伴发热☃三天"            # the snowman is not in the vocabulary -> [UNK]
+    enc = tok(text, return_special_tokens_mask=True, return_offsets_mapping=True)
+    ids, offsets, special = enc["input_ids"], enc["offset_mapping"], enc["special_tokens_mask"]
+    assert tok.unk_token_id in ids
+    n = len(ids)
+    rng = np.random.default_rng(0)
+    sequences = [
+        [1, 2, 2, 1, 2, 0, 3, 4, 0, 0, 7],      # B I I B I O B I O O B
+        [2, 2, 4, 4, 6, 0, 0, 1, 1, 1, 8],      # I-runs of different types, B B B
+        [0] * 11, [3] * 11, [5, 6, 5, 6, 5, 6, 5, 6, 5, 6, 5],
+    ] + [rng.integers(0, len(nc.LABELS), size=11).tolist() for _ in range(20)]
+    for labels in sequences:
+        labels = (labels * 3)[:n - 2]
+        scores = np.full((n, len(nc.LABELS)), 0.01, np.float32)
+        conf = rng.uniform(0.4, 0.9, size=n).astype(np.float32)
+        for t, lab in enumerate(labels):
+            scores[t + 1, lab] = conf[t + 1]                      # position 0 / n-1 are [CLS] / [SEP]
+        pre = pipe.gather_pre_entities(text, np.asarray(ids), scores, offsets, np.asarray(special), AggregationStrategy.SIMPLE)
+        ref = [g for g in pipe.aggregate(pre, AggregationStrategy.SIMPLE) if g["entity_group"] != "O"]
+        got = TC.aggregate_simple(tok, id2label, text, ids, scores, offsets, special)
+        nc.same_groups(got, ref, score_tol=1e-7)
