@@ -8,6 +8,14 @@ text -- with the BERT forward and the classifier head running in libicdrag.so on
 the "simple" grouping of adjacent tokens stay on the host, as they do inside the transformers pipeline
 (third party, transformers TokenClassificationPipeline: postprocess / gather_pre_entities / aggregate /
 group_entities; restated here, checked against the pipeline itself in tests/test_ner_*.py).
+
+Long texts.  The kernels take sequences of at most 128 tokens; the reference pipeline reads up to the model's 512.
+A text that does not fit one window is cut into overlapping windows (the tokenizer's own overflow mechanism,
+`stride` tokens of overlap) that go through the GPU as one batch, and the windows' entities are merged with the
+pipeline's rule for exactly this case (aggregate_overlapping_entities: of two overlapping entities the longer
+wins, then the higher score) -- the algorithm of ``pipeline(..., stride=n)``.  Tokens beyond the reference's own
+512-token horizon are dropped, as they are there.  Texts of up to 126 tokens (every diagnosis string in the
+reference's data) take the single-window path and are unaffected.
 """
 from __future__ import annotations
 
@@ -34,6 +42,26 @@ def softmax_rows(logits: np.ndarray) -> np.ndarray:
     maxes = np.max(logits, axis=-1, keepdims=True)
     e = np.exp(logits - maxes)
     return e / e.sum(axis=-1, keepdims=True)
+
+
+def merge_overlapping(entities: List[dict]) -> List[dict]:
+    """transformers' aggregate_overlapping_entities: entities of all windows sorted by start; of two that overlap
+    the longer one survives, at equal length the higher score."""
+    if not entities:
+        return entities
+    entities = sorted(entities, key=lambda x: x["start"])
+    out = []
+    prev = entities[0]
+    for ent in entities:
+        if prev["start"] <= ent["start"] < prev["end"]:
+            cur_len, prev_len = ent["end"] - ent["start"], prev["end"] - prev["start"]
+            if cur_len > prev_len or (cur_len == prev_len and ent["score"] > prev["score"]):
+                prev = ent
+        else:
+            out.append(prev)
+            prev = ent
+    out.append(prev)
+    return out
 
 
 def aggregate_simple(tokenizer, id2label: Dict[int, str], sentence: str, input_ids: Sequence[int],
@@ -83,7 +111,7 @@ class TokenClassifierEngine:
     def __init__(self, model_name_or_path: Optional[str] = None, device: Union[str, int, None] = None, *,
                  encoder: Optional[EncoderEngine] = None, head_weight: Optional[np.ndarray] = None,
                  head_bias: Optional[np.ndarray] = None, id2label: Optional[Dict[int, str]] = None,
-                 tokenizer=None, max_tokens: int = 1024 * 128):
+                 tokenizer=None, max_tokens: int = 1024 * 128, stride: int = 16, horizon: int = 512):
         if encoder is None:
             path = W.resolve_model_dir(model_name_or_path)
             cfg, blob, _meta = W.load_model_dir(path)
@@ -105,6 +133,8 @@ class TokenClassifierEngine:
         if len(self.id2label) != n:
             raise ValueError("id2label does not match the classifier head")
         self.max_seq_length = self.encoder.max_seq_length   # kernel limit 128 tokens per sequence
+        self.stride = int(stride)                            # overlap of the windows of a long text, in tokens
+        self.horizon = int(horizon)                          # the reference pipeline truncates at model_max_length
 
     def __call__(self, inputs, **_ignored):
         single = isinstance(inputs, str)
@@ -116,11 +146,21 @@ class TokenClassifierEngine:
         if not texts:
             return []
         enc = self.tokenizer(list(texts), padding=False, truncation=True, max_length=self.max_seq_length,
+                             stride=self.stride, return_overflowing_tokens=True,
                              return_special_tokens_mask=True, return_offsets_mapping=True,
                              return_attention_mask=False, return_token_type_ids=False)
-        ids = enc["input_ids"]
-        results: List[Optional[List[dict]]] = [None] * len(texts)
-        order = sorted(range(len(ids)), key=lambda j: -len(ids[j]))
+        ids = enc["input_ids"]                                   # one entry per WINDOW
+        owner = enc["overflow_to_sample_mapping"]                # window -> text
+        # windows that start beyond the reference's 512-token horizon are dropped (it never sees those tokens)
+        step = max(1, self.max_seq_length - 2 - self.stride)
+        seen, keep = {}, []
+        for w, t in enumerate(owner):
+            k = seen.get(t, 0)
+            seen[t] = k + 1
+            if k * step < max(1, self.horizon - 2):
+                keep.append(w)
+        per_window: Dict[int, List[dict]] = {}
+        order = sorted(keep, key=lambda w: -len(ids[w]))
         lo = 0
         while lo < len(order):
             S = max(1, len(ids[order[lo]]))
@@ -128,17 +168,25 @@ class TokenClassifierEngine:
             idx = order[lo:lo + B]
             mat = np.zeros((B, S), np.int32)
             lens = np.zeros((B,), np.int32)
-            for r, j in enumerate(idx):
-                mat[r, :len(ids[j])] = ids[j]
-                lens[r] = len(ids[j])
+            for r, w in enumerate(idx):
+                mat[r, :len(ids[w])] = ids[w]
+                lens[r] = len(ids[w])
             logits = self.encoder.token_logits(mat, lens)
-            for r, j in enumerate(idx):
+            for r, w in enumerate(idx):
                 n = int(lens[r])
                 scores = softmax_rows(logits[r, :n].astype(np.float32))
-                results[j] = aggregate_simple(self.tokenizer, self.id2label, texts[j], ids[j], scores,
-                                              enc["offset_mapping"][j], enc["special_tokens_mask"][j])
+                per_window[w] = aggregate_simple(self.tokenizer, self.id2label, texts[owner[w]], ids[w], scores,
+                                                 enc["offset_mapping"][w], enc["special_tokens_mask"][w])
             lo += B
-        return results  # type: ignore[return-value]
+        results: List[List[dict]] = [[] for _ in texts]
+        windows_of: Dict[int, int] = {}
+        for w in keep:
+            results[owner[w]].extend(per_window[w])
+            windows_of[owner[w]] = windows_of.get(owner[w], 0) + 1
+        for t, n_win in windows_of.items():
+            if n_win > 1:
+                results[t] = merge_overlapping(results[t])
+        return results
 
     def close(self) -> None:
         self.encoder.close()

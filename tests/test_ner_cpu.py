@@ -101,3 +101,37 @@ def test_grouping_rules_match_pipeline_on_crafted_label_sequences(tiny):
         ref = [g for g in pipe.aggregate(pre, AggregationStrategy.SIMPLE) if g["entity_group"] != "O"]
         got = TC.aggregate_simple(tok, id2label, text, ids, scores, offsets, special)
         nc.same_groups(got, ref, score_tol=1e-7)
+
+
+def test_long_texts_go_through_overlapping_windows_like_pipeline_stride(tiny):
+    """A text longer than one 128-token window: the engine cuts it into overlapping windows and merges their entities
+    with the pipeline's own overlap rule -- the algorithm of pipeline(..., stride=n) with a 128-token model limit."""
+    from transformers import pipeline
+    model, tok = tiny
+    TC = importlib.import_module("rag-project-icd10_b200.engine.token_classifier")
+    eng = TC.TokenClassifierEngine(encoder=_StubEncoder(model, tok), head_weight=np.zeros((len(nc.LABELS), 64), np.float32),
+                                   head_bias=np.zeros(len(nc.LABELS), np.float32), id2label=dict(enumerate(nc.LABELS)),
+                                   tokenizer=tok, stride=16)
+    long_text = ",".join(nc.TEXTS * 5)                       # ~ 400 tokens: four windows
+    assert len(tok(long_text)["input_ids"]) > 300
+    old = tok.model_max_length
+    tok.model_max_length = 128
+    try:
+        ref_pipe = pipeline("ner", model=model, tokenizer=tok, aggregation_strategy="simple", device=-1, stride=16)
+        ref = ref_pipe(long_text)
+    finally:
+        tok.model_max_length = old
+    got = eng(long_text)
+    assert len(ref) > 20
+    nc.same_groups(got, ref, score_tol=1e-5)
+    # a batch mixing short and long texts keeps every text's own result
+    mixed = eng([nc.TEXTS[0], long_text, nc.TEXTS[1]])
+    nc.same_groups(mixed[1], ref, score_tol=1e-5)
+    nc.same_groups(mixed[0], eng(nc.TEXTS[0]), 1e-6)
+    nc.same_groups(mixed[2], eng(nc.TEXTS[1]), 1e-6)
+    # beyond the reference's 512-token horizon nothing is read
+    huge = ",".join(nc.TEXTS * 12)
+    assert len(tok(huge)["input_ids"]) > 700
+    ends = [g["end"] for g in eng(huge)]
+    cut = tok(huge, truncation=True, max_length=640, return_offsets_mapping=True)["offset_mapping"][-2][1]
+    assert ends and max(ends) <= cut
