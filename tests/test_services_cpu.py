@@ -142,3 +142,29 @@ def test_tokenizers_read_the_vocab_file(tmp_path):
         ids = tok(texts[1])["input_ids"]
         assert ids[0] == 101 and ids[-1] == 102 and 100 not in ids and len(set(ids)) >= 8
     assert a(texts)["input_ids"] == b(texts)["input_ids"]
+
+
+def test_header_is_plain_c_and_matches_the_library(tmp_path):
+    """include/icdrag.h is the drop-in boundary: it must compile as C (no C++/torch/CUDA types in the signatures) and a
+    C program that references every declared function must link against libicdrag.so."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "icdrag.h")
+    src = open(hdr, encoding="utf-8").read()
+    names = sorted(set(re.findall(r"\b(icd_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", src, flags=re.S))))
+    native = importlib.import_module("rag-project-icd10_b200._native")
+    assert names == sorted(native.SYMBOLS), (set(names) ^ set(native.SYMBOLS))
+    c = tmp_path / "use_all.c"
+    c.write_text('#include "icdrag.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n  fn p[] = {' +
+                 ", ".join(f"(fn){n}" for n in names) + "};\n  printf(\"%d %d\\n\", (int)(sizeof p / sizeof p[0]), icd_version());\n  return 0;\n}\n")
+    exe = tmp_path / "use_all"
+    libdir = os.path.dirname(native.LIB_PATH)
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.dirname(hdr), str(c), "-o", str(exe),
+                          "-L", libdir, "-licdrag", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.split()[0] == str(len(names)), (run.stdout, run.stderr)
