@@ -16,8 +16,10 @@
  *     cudaPointerGetAttributes. Host inputs are copied in, host outputs copied back, inside
  *     the call (that is the "e2e" path bench.py times).
  *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). With
- *     sync=0 and device buffers the call returns after enqueue; with host buffers or sync=1
- *     it returns when the results are in place.
+ *     sync=0 and device OUTPUT buffers the call returns after enqueue (host INPUT buffers must
+ *     then stay untouched until the stream has consumed them: pageable ones are staged before
+ *     the call returns, pinned ones are read asynchronously); with host output buffers or
+ *     sync=1 it returns when the results are in place.
  *   - one in-flight call per handle; distinct handles are independent.
  *   - there is NO CPU fallback: without a CUDA device every create call fails with
  *     ICD_E_CUDA.
@@ -182,6 +184,33 @@ int icd_encoder_set_token_head(icd_encoder* enc, const float* weight, const floa
  * >= lens[b] hold the logits of padding tokens and are ignored by the caller, like the pipeline ignores them. */
 int icd_encoder_token_logits(icd_encoder* enc, const int32_t* ids, const int32_t* lens, int B, int S,
                              float* out, void* stream, int sync);
+
+/* ---------------------------------------------------------------- host tokeniser (encoder feeder) ------
+ * Replaces the tokenisation step inside SentenceTransformer.encode (the model directory's BertTokenizerFast, reached
+ * from services/embedding_service.py:81,97-102,120): BERT normaliser -> whitespace / punctuation split -> WordPiece
+ * -> [CLS] ... [SEP], multi-threaded on the host, writing the int32 id rows icd_encoder_forward reads.
+ *   tokens        the vocabulary, one token per line ('\n'-terminated UTF-8), n_tokens lines; ids[i] = id of line i
+ *   char_class    [65536] per BMP code point: bits 0-1 kind (0 map, 1 whitespace, 2 remove, 3 fallback), bit 2 = CJK
+ *                 ideograph (isolated), bit 3 = punctuation when it appears as an OUTPUT character
+ *   map_offsets   [65537] / map_pool [pool_len]: normalised replacement code points of every kind-0 code point
+ * (rag-project-icd10_b200/engine/tokenizer.py builds the tables from the Unicode database and decides which code
+ * points are left to the wrapped reference tokenizer.) */
+typedef struct icd_tokenizer icd_tokenizer;
+int icd_tokenizer_create(const char* tokens, int64_t tokens_bytes, const int32_t* ids, int64_t n_tokens,
+                         const uint8_t* char_class, const uint32_t* map_offsets, const uint32_t* map_pool,
+                         int64_t pool_len, icd_tokenizer** out);
+int icd_tokenizer_destroy(icd_tokenizer* tok);
+/* texts: n UTF-8 strings joined by single NUL bytes (nbytes in total, no trailing NUL).  Row i of ids (row_stride
+ * int32 per row, >= max_len) receives lens[i] ids including [CLS] / [SEP], truncated to max_len; entries past lens[i]
+ * are left untouched.  needs_fallback[i] = 1 (and lens[i] = 0) when sentence i must go through the reference
+ * tokenizer instead (fallback code point, supplementary plane, malformed UTF-8, literal special token).
+ * threads <= 0: all hardware threads. */
+int icd_tokenizer_encode(const icd_tokenizer* tok, const char* texts, int64_t nbytes, int64_t n, int max_len,
+                         int32_t* ids, int row_stride, int32_t* lens, uint8_t* needs_fallback, int threads);
+/* gather rows[b] (b < B) of such an id table into a zero-padded [B, S] batch + lens[B]: the ids / lens arguments of
+ * icd_encoder_forward (host buffers; pinned ones make the H2D copy asynchronous) */
+int icd_pack_batch(const int32_t* ids, int row_stride, const int32_t* lens, const int64_t* rows, int B, int S,
+                   int32_t* out_ids, int32_t* out_lens);
 
 #ifdef __cplusplus
 }

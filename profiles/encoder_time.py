@@ -2,7 +2,7 @@
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-E = importlib.import_module("rag-project-icd10_b200.engine.encoder")
+import bench as E
 B, S = int(os.environ.get("ENC_B", 4096)), int(os.environ.get("ENC_S", 64))
 reps = int(os.environ.get("ENC_REPS", 20))
 eng = E.synthetic_engine(device=0, max_tokens=B * S)

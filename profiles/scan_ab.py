@@ -9,8 +9,10 @@ N = importlib.import_module("rag-project-icd10_b200._native")
 VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").VectorIndex
 rows, B, k = int(os.environ.get("ROWS", 100_000_000)), int(os.environ.get("BATCH", 1024)), 10
 steps = int(os.environ.get("STEPS", 5))
+warm = int(os.environ.get("WARM", 2))
 variants = [v for v in os.environ.get("VARIANTS", "scan_pair=-1;scan_pair=0").split(";") if v]
-DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0)
+DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_kbs_pair=6, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0,
+                scan_generic=0)
 dev = torch.device("cuda", 0)
 table, levels = bench.make_corpus(torch, rows, dev, 1234)
 q = bench.make_queries(torch, B, dev)
@@ -24,7 +26,7 @@ for rep in range(2):
     for v in variants:
         N.tune(**DEFAULTS)
         N.tune(**{kv.split("=")[0]: int(kv.split("=")[1]) for kv in v.split(",")})
-        for _ in range(2):
+        for _ in range(warm):
             idx.search(q, k, out=out, stream=st.cuda_stream, sync=False)
         torch.cuda.synchronize()
         idx.set_timing(True)

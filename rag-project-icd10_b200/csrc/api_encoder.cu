@@ -462,7 +462,10 @@ int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens,
   if (host_out) {
     ICD_CUDA(cudaMemcpyAsync(out, d_out, (size_t)B * H * (out_dtype == ICD_F32 ? 4 : 2), cudaMemcpyDeviceToHost, st));
   }
-  if (sync || host_out || !is_device_ptr(ids) || !is_device_ptr(lens)) ICD_CUDA(cudaStreamSynchronize(st));
+  // host inputs were handed to cudaMemcpyAsync above: pageable buffers are staged before that call returns, pinned
+  // ones are read when the stream gets there -- with sync = 0 the caller keeps them untouched until then (the feeder
+  // in engine/encoder.py double-buffers them behind events)
+  if (sync || host_out) ICD_CUDA(cudaStreamSynchronize(st));
   return ICD_OK;
 }
 
@@ -513,7 +516,10 @@ int icd_encoder_token_logits(icd_encoder* e, const int32_t* ids, const int32_t* 
   ICD_TRY(encode_hidden(e, ids, lens, B, S, st, &final_h, &d_lens));
   ICD_TRY(launch_token_head(final_h, B * S, e->head_w, e->head_b, L, d_out, st));
   if (host_out) ICD_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, st));
-  if (sync || host_out || !is_device_ptr(ids) || !is_device_ptr(lens)) ICD_CUDA(cudaStreamSynchronize(st));
+  // host inputs were handed to cudaMemcpyAsync above: pageable buffers are staged before that call returns, pinned
+  // ones are read when the stream gets there -- with sync = 0 the caller keeps them untouched until then (the feeder
+  // in engine/encoder.py double-buffers them behind events)
+  if (sync || host_out) ICD_CUDA(cudaStreamSynchronize(st));
   return ICD_OK;
 }
 

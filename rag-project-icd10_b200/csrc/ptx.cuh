@@ -228,6 +228,43 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+// ---- lean forms for fully unrolled issue loops: the 64-bit shared-memory descriptor is passed as (lo, hi) words so
+// that stepping through a stage is one 32-bit add on the low word (start-address field, no carry out of its 14 bits),
+// and the accumulate flag is a compile-time constant (r02a: the generic scan loop spent ~73 cycles of uniform-datapath
+// instructions per 64-cycle MMA -- 16.6 instructions per tcgen05.mma -- and was ISSUE-bound)
+constexpr uint32_t kDescHiK128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_k128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <int NC, int ACC>
+__device__ __forceinline__ void mma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc) {
+  if (NC == 1)
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %4, 0;\nmov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(ACC), "n"(kDescHiK128)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %4, 0;\nmov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "n"(ACC), "n"(kDescHiK128)
+        : "memory");
+}
+template <int NC, int ACC>
+__device__ __forceinline__ void mma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  if (NC == 1)
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %4, 0;\nmov.b64 ad, {%1, %5};\nmov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC), "n"(kDescHiK128)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 ad, bd;\nsetp.ne.b32 p, %4, 0;\nmov.b64 ad, {%1, %5};\nmov.b64 bd, {%2, %5};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "n"(ACC), "n"(kDescHiK128)
+        : "memory");
+}
+
 // instruction descriptor, kind::f16, bf16 x bf16 -> fp32, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4)                     // D format: f32

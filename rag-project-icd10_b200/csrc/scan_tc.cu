@@ -105,8 +105,13 @@ __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, i
   return ls[(kc - 1) * BM];
 }
 
-// BN = table rows per accumulator tile (MMA N); NC = CTAs per MMA (2 = CTA pair, cta_group::2)
-template <int BN, int NC>
+// BN = table rows per accumulator tile (MMA N); NC = CTAs per MMA (2 = CTA pair, cta_group::2).
+// KBS / NKBT > 0: the stage shape (K blocks per stage) and the TMEM / shared-memory split of the query tile are
+// compile-time constants for dim = 768, so the MMA issue loop unrolls into ~4 instructions per tcgen05.mma.  The generic
+// loop (KBS = 0: run-time kbs / nkb_tmem, 64-bit descriptor arithmetic, TS-or-SS branch per MMA) costs 16.6 instructions
+// = ~73 issue cycles per 64-cycle MMA (ncu r02a, B = 256: the elected thread was busy issuing 73 % of the time, waiting
+// for data 3 % and for the epilogue 14 %): the tensor pipe was bounded by instruction issue, not by operands.
+template <int BN, int NC, int KBS, int NKBT>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kBoxBytes = (BN / NC) * BK * 2;  // this CTA's share of one BN x 64 bf16 tile
@@ -265,7 +270,58 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (prog && lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(prog + me), "r"(0x7fffffff) : "memory");
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (rank == 0 && ptx::elect_one()) {
+    if (KBS > 0 && rank == 0 && ptx::elect_one()) {
+      // ---- specialised issue loop (dim = 768: 12 K blocks, KBS per stage, the first NKBT of the query tile in TMEM)
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * NC, BN);
+      constexpr int kNKB = 12;
+      constexpr int kKBS = KBS > 0 ? KBS : 1;
+      constexpr uint32_t kStageStep = (uint32_t)(kKBS * kBoxBytes) >> 4;  // descriptor units (16 bytes) per stage
+      const uint32_t stage_lo0 = ptx::desc_lo_k128(ptx::smem_u32(stage_base));
+      const uint32_t qtail_lo = ptx::desc_lo_k128(ptx::smem_u32(q_tail));
+      const uint32_t full0 = ptx::smem_u32(&full_bar[0]), empty0 = ptx::smem_u32(&empty_bar[0]);
+      const uint32_t nst = (uint32_t)p.nst;
+      const bool two_acc = p.nacc == 2;
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int64_t t = t0; t < t1; ++t, ++it) {
+        const int buf = two_acc ? (it & 1) : 0;
+        const uint32_t use = two_acc ? (uint32_t)(it >> 1) : (uint32_t)it;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[buf]), (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(p.acc_col0 + buf * BN);
+#pragma unroll
+        for (int s = 0; s < kNKB / kKBS; ++s) {
+          ptx::mbar_wait(full0 + stage * 8, phase);
+          ptx::tc_fence_after();
+          const uint32_t b_lo = stage_lo0 + stage * kStageStep;
+#pragma unroll
+          for (int j = 0; j < kKBS; ++j) {
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const int kb = s * kKBS + j;                                     // compile-time after unrolling
+              const uint32_t boff = (uint32_t)(j * (kBoxBytes >> 4) + k4 * 2);  // +2 per 32 bytes of K, +tile per K block
+              if (kb < NKBT) {
+                const uint32_t a_tmem = tmem_base + (uint32_t)((kb * (BK / 16) + k4) * 8);
+                if (s == 0 && j == 0 && k4 == 0) ptx::mma_ts_lo<NC, 0>(d_tmem, a_tmem, b_lo + boff, idesc);
+                else ptx::mma_ts_lo<NC, 1>(d_tmem, a_tmem, b_lo + boff, idesc);
+              } else {
+                const uint32_t a_lo = qtail_lo + (uint32_t)((kb - NKBT) * (kQTileBytes >> 4) + k4 * 2);
+                if (s == 0 && j == 0 && k4 == 0) ptx::mma_ss_lo<NC, 0>(d_tmem, a_lo, b_lo + boff, idesc);
+                else ptx::mma_ss_lo<NC, 1>(d_tmem, a_lo, b_lo + boff, idesc);
+              }
+            }
+          }
+          if (NC == 1) ptx::tc_commit(empty0 + stage * 8);
+          else ptx::tc_commit_pair(empty0 + stage * 8, 3);
+          if (++stage == nst) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (NC == 1) ptx::tc_commit(ptx::smem_u32(&tfull_bar[buf]));
+        else ptx::tc_commit_pair(ptx::smem_u32(&tfull_bar[buf]), 3);
+      }
+    } else if (KBS == 0 && rank == 0 && ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * NC, BN);
       const uint64_t qtail_desc0 = ptx::make_desc_k128(ptx::smem_u32(q_tail));
       int stage = 0;
@@ -478,7 +534,7 @@ static int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, gen;
+  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
@@ -489,6 +545,7 @@ struct Tunables {
     qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always
     pair = env_int("ICD_SCAN_PAIR", -1);      // CTA pairs: -1 auto (even number of query tiles >= 2), 0 off
     qtmem = env_int("ICD_SCAN_QTMEM", 0);      // K blocks of the query tile kept in TMEM when split (0 = all that fit: 8)
+    generic = env_int("ICD_SCAN_GENERIC", 0);   // 1 = always the generic (run-time shape) issue loop: A/B only
     gen = 0;
   }
 };
@@ -511,6 +568,7 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_qsplit")) t.qsplit = value;
   else if (!strcmp(key, "scan_pair")) t.pair = value;
   else if (!strcmp(key, "scan_qtmem")) t.qtmem = std::max(0, value);
+  else if (!strcmp(key, "scan_generic")) t.generic = value != 0;
   else return ICD_E_ARG;
   ++t.gen;  // tensor maps depend on bn / kbs: indexes rebuild theirs when the generation moves
   return ICD_OK;
@@ -550,6 +608,7 @@ template <int BN>
 static int resident_pairs(size_t smem) {
   static int cached = 0;
   if (cached) return cached;
+  cudaFuncSetAttribute(scan_tc_kernel<BN, 2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kSMs);
   cfg.blockDim = dim3(kThreads);
@@ -562,12 +621,39 @@ static int resident_pairs(size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, scan_tc_kernel<BN, 2>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, scan_tc_kernel<BN, 2, 0, 0>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     n = 0;
   }
   cached = std::max(0, n);
   return cached;
+}
+
+template <int BN, int NC, int KBS, int NKBT>
+static int launch_one(const CUtensorMap& tmap, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kernel = scan_tc_kernel<BN, NC, KBS, NKBT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ICD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (NC == 2) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  ICD_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, p));
+  count_launch();
+  return ICD_OK;
 }
 
 template <int BN>
@@ -579,8 +665,6 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   // launch fills the SMs (G * T_launch <= 148) and at most tmax CTAs share one row stream
   const int n_launch = (T_total + scan_tmax() - 1) / scan_tmax();
   const int T_launch = (T_total + n_launch - 1) / n_launch;
-  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  ICD_CUDA(cudaFuncSetAttribute(scan_tc_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   // CTA pairs: every launch must hold an even number of query tiles (the pair = two neighbouring tiles)
   bool pair = BN == 128 && tun().pair != 0 && T_launch >= 2 && T_launch % 2 == 0 && T_total % T_launch == 0;
   int sms = kSMs;
@@ -667,25 +751,14 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.tstride = tstride;
     p.drift = scan_drift();
     p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64) ? a.progress + (size_t)launch * kSMs : nullptr;
-    if (pair) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(G * p.T);
-      cfg.blockDim = dim3(kThreads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      ICD_CUDA(cudaLaunchKernelEx(&cfg, scan_tc_kernel<BN, 2>, tmap, p));
-    } else {
-      scan_tc_kernel<BN, 1><<<G * p.T, kThreads, smem, st>>>(tmap, p);
-    }
-    count_launch();
-    ICD_CUDA(cudaGetLastError());
+    // specialised issue loops for the shapes the launcher actually picks at dim = 768 (everything else: generic)
+    const bool spec = BN == 128 && a.dim == 768 && nkb_tmem == 8 && tun().generic == 0;
+    if (pair && spec && kbs == 6) ICD_TRY((launch_one<BN, 2, 6, 8>(tmap, p, G * p.T, smem, st)));
+    else if (pair && spec && kbs == 3) ICD_TRY((launch_one<BN, 2, 3, 8>(tmap, p, G * p.T, smem, st)));
+    else if (pair) ICD_TRY((launch_one<BN, 2, 0, 0>(tmap, p, G * p.T, smem, st)));
+    else if (spec && kbs == 3) ICD_TRY((launch_one<BN, 1, 3, 8>(tmap, p, G * p.T, smem, st)));
+    else if (spec && kbs == 2) ICD_TRY((launch_one<BN, 1, 2, 8>(tmap, p, G * p.T, smem, st)));
+    else ICD_TRY((launch_one<BN, 1, 0, 0>(tmap, p, G * p.T, smem, st)));
   }
   return ICD_OK;
 }

@@ -8,20 +8,26 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
 
 from .. import _native as N
 from . import weights as W
+from .tokenizer import NativeTokenizer
 
 MAX_S = 128  # kernel limit == sentence-transformers max_seq_length of text2vec-base-chinese
+FEED_CHUNK = 32768   # sentences tokenised / length-bucketed / copied back as one unit of the feeder pipeline
+SMALL_BATCH = 256    # up to this many sentences take the direct path (one tokeniser call, synchronous launches)
 
 
 class EncoderEngine:
     def __init__(self, model_name_or_path: Optional[str] = None, device: Union[str, int, None] = None, *,
                  cfg: Optional[N.BertCfg] = None, blob: Optional[np.ndarray] = None, tokenizer=None,
-                 max_seq_length: int = 128, max_tokens: int = 4096 * 64):
+                 max_seq_length: int = 128, max_tokens: int = 4096 * 64, vocab_path: Optional[str] = None,
+                 host_threads: Optional[int] = None):
         N.require_gpu()
         self.device_index = _device_index(device)
         if blob is None:
@@ -36,6 +42,11 @@ class EncoderEngine:
         self.tokenizer = tokenizer
         self.max_seq_length = min(int(max_seq_length), MAX_S, cfg.max_position)
         self.max_tokens = int(max_tokens)
+        self.vocab_path = vocab_path
+        self.last_stats: dict = {}
+        self._feed = None          # pinned staging buffers, created on first bulk encode
+        # host feeder: multi-threaded WordPiece in libicdrag for plain BERT tokenizers, the tokenizer itself otherwise
+        self._ntok = NativeTokenizer(tokenizer, threads=host_threads) if hasattr(tokenizer, "backend_tokenizer") else None
         self._h = C.c_void_p()
         blob = np.ascontiguousarray(blob, np.float32)
         N.check(N.lib().icd_encoder_create(N.buf_ptr(blob), blob.size, C.byref(cfg), self.device_index,
@@ -49,13 +60,15 @@ class EncoderEngine:
                convert_to_numpy: bool = True, **_ignored):
         single = isinstance(sentences, str)
         items: List[str] = [sentences] if single else list(sentences)
-        out = np.zeros((len(items), self.cfg.hidden), np.float32)
-        if items:
-            ids = self.tokenize(items)
-            self._encode_ids(ids, out, normalize_embeddings)
+        if not items:
+            return np.zeros((0, self.cfg.hidden), np.float32)
+        out = self._encode_texts(items, normalize_embeddings)
         return out[0] if single else out
 
     def close(self) -> None:
+        if getattr(self, "_feed", None) is not None:
+            self._feed["pool"].shutdown(wait=True)
+            self._feed = None
         if getattr(self, "_h", None) is not None and self._h.value:
             N.lib().icd_encoder_destroy(self._h)
             self._h = C.c_void_p()
@@ -68,27 +81,160 @@ class EncoderEngine:
 
     # ---------------------------------------------------------------- host side
     def tokenize(self, texts: Sequence[str]) -> List[List[int]]:
-        enc = self.tokenizer(list(texts), padding=False, truncation=True, max_length=self.max_seq_length,
-                             add_special_tokens=True, return_attention_mask=False, return_token_type_ids=False)
-        return enc["input_ids"]
+        ids, lens = self._token_table(list(texts))
+        return [ids[i, :lens[i]].tolist() for i in range(len(lens))]
 
-    def _encode_ids(self, ids: List[List[int]], out: np.ndarray, normalise: bool) -> None:
-        """Length-bucketed batches: sort by token count, cut where B*S would exceed max_tokens."""
-        order = sorted(range(len(ids)), key=lambda j: -len(ids[j]))
-        lo = 0
-        while lo < len(order):
-            S = max(1, len(ids[order[lo]]))
-            B = max(1, min(len(order) - lo, self.max_tokens // S))
-            idx = order[lo:lo + B]
-            mat = np.zeros((B, S), np.int32)
-            lens = np.zeros((B,), np.int32)
-            for r, j in enumerate(idx):
-                row = ids[j]
-                mat[r, :len(row)] = row
-                lens[r] = len(row)
-            res = self.forward_ids(mat, lens, normalise=normalise)
-            out[idx] = res
+    def _token_table(self, texts: List[str]):
+        """ids [n, max_seq_length] int32 (row i valid up to lens[i]) and lens [n] int32."""
+        L = self.max_seq_length
+        if self._ntok is not None:
+            return self._ntok.encode(texts, L)
+        enc = self.tokenizer(texts, padding=False, truncation=True, max_length=L, add_special_tokens=True,
+                             return_attention_mask=False, return_token_type_ids=False)["input_ids"]
+        ids = np.zeros((len(enc), L), np.int32)
+        lens = np.zeros((len(enc),), np.int32)
+        for i, row in enumerate(enc):
+            lens[i] = len(row)
+            ids[i, :len(row)] = row
+        return ids, lens
+
+    def _pack(self, ids, lens, rows, S, out_ids, out_lens) -> None:
+        if self._ntok is not None:
+            self._ntok.pack(ids, lens, rows, S, out_ids, out_lens)
+        else:
+            out_ids[:] = ids[rows, :S]
+            out_lens[:] = np.minimum(lens[rows], S)
+            out_ids[np.arange(S)[None, :] >= out_lens[:, None]] = 0
+
+    def _batches(self, lens: np.ndarray):
+        """Length-bucketed batches over one chunk: rows by descending token count, cut where B*S would exceed
+        max_tokens.  Yields (rows, S)."""
+        order = np.argsort(-lens.astype(np.int64), kind="stable")
+        lo, n = 0, len(order)
+        while lo < n:
+            S = max(1, int(lens[order[lo]]))
+            B = max(1, min(n - lo, self.max_tokens // S))
+            yield order[lo:lo + B], S
             lo += B
+
+    def _encode_texts(self, items: List[str], normalise: bool) -> np.ndarray:
+        n, H = len(items), int(self.cfg.hidden)
+        if n <= SMALL_BATCH:
+            # direct path (the reference's live pattern is batch 1): one tokeniser call, synchronous launches
+            t0 = time.perf_counter()
+            ids, lens = self._token_table(items)
+            t1 = time.perf_counter()
+            out = np.empty((n, H), np.float32)
+            for rows, S in self._batches(lens):
+                mat = np.empty((len(rows), S), np.int32)
+                bl = np.empty((len(rows),), np.int32)
+                self._pack(ids, lens, rows, S, mat, bl)
+                out[rows] = self.forward_ids(mat, bl, normalise=normalise)
+            self.last_stats = {"sentences": n, "tokens": int(lens.sum()), "tokenize_s": t1 - t0,
+                               "encode_s": time.perf_counter() - t1, "h2d_bytes": int(lens.sum()) * 4,
+                               "tokenizer": self._tokenizer_kind()}
+            return out
+        return self._encode_pipelined(items, normalise)
+
+    def _tokenizer_kind(self) -> str:
+        if self._ntok is not None and self._ntok.native:
+            return f"native WordPiece, {self._ntok.threads} host threads ({self._ntok.fallbacks} sentences via the wrapped tokenizer)"
+        return "wrapped tokenizer (transformers)"
+
+    def _feed_buffers(self):
+        """Pinned staging, allocated once: two id / length slots (a batch is packed while the previous one is in
+        flight) and two output slots (a chunk's embeddings are copied back while the next chunk runs)."""
+        if self._feed is None:
+            import torch
+            dev = torch.device("cuda", self.device_index)
+            f = {"dev": dev, "stream": torch.cuda.Stream(device=dev)}
+            f["ids"] = [torch.empty((self.max_tokens,), dtype=torch.int32).pin_memory() for _ in range(2)]
+            f["lens"] = [torch.empty((self.max_tokens,), dtype=torch.int32).pin_memory() for _ in range(2)]
+            f["in_ev"] = [torch.cuda.Event() for _ in range(2)]
+            f["out"] = [torch.empty((FEED_CHUNK, int(self.cfg.hidden)), dtype=torch.float32).pin_memory() for _ in range(2)]
+            f["out_ev"] = [torch.cuda.Event() for _ in range(2)]
+            f["d_sorted"] = torch.empty((FEED_CHUNK, int(self.cfg.hidden)), dtype=torch.float32, device=dev)
+            f["inv"] = [torch.empty((FEED_CHUNK,), dtype=torch.int64).pin_memory() for _ in range(2)]
+            f["d_inv"] = torch.empty((FEED_CHUNK,), dtype=torch.int64, device=dev)
+            f["pool"] = ThreadPoolExecutor(max_workers=1)
+            self._feed = f
+        return self._feed
+
+    def _encode_pipelined(self, items: List[str], normalise: bool) -> np.ndarray:
+        """The feeder (SURVEY section 7 "hard part"): while the GPU encodes chunk c, a worker thread tokenises chunk
+        c+1 (the C call releases the GIL) and the main thread packs length-bucketed batches into pinned slots; every
+        launch is asynchronous on one stream, embeddings land in sorted order on the device, are un-sorted there and
+        leave through pinned buffers while the next chunk runs."""
+        import torch
+        f = self._feed_buffers()
+        n, H = len(items), int(self.cfg.hidden)
+        out = np.empty((n, H), np.float32)
+        stream = f["stream"]
+        chunks = [(lo, min(n, lo + FEED_CHUNK)) for lo in range(0, n, FEED_CHUNK)]
+        stats = {"sentences": n, "tokens": 0, "h2d_bytes": 0, "tokenize_wait_s": 0.0, "pack_s": 0.0, "slot_wait_s": 0.0,
+                 "copy_out_s": 0.0, "batches": 0}
+        t_all = time.perf_counter()
+        fut = f["pool"].submit(self._token_table, items[chunks[0][0]:chunks[0][1]])
+        pending = None       # (chunk index, lo, hi) whose output copy is in flight
+        slot = 0
+
+        def finish(p):
+            ci, lo, hi = p
+            t0 = time.perf_counter()
+            f["out_ev"][ci & 1].synchronize()
+            np.copyto(out[lo:hi], f["out"][ci & 1].numpy()[:hi - lo])
+            stats["copy_out_s"] += time.perf_counter() - t0
+
+        with torch.cuda.stream(stream):
+            for ci, (lo, hi) in enumerate(chunks):
+                t0 = time.perf_counter()
+                ids, lens = fut.result()
+                stats["tokenize_wait_s"] += time.perf_counter() - t0
+                if ci + 1 < len(chunks):
+                    fut = f["pool"].submit(self._token_table, items[chunks[ci + 1][0]:chunks[ci + 1][1]])
+                m = hi - lo
+                stats["tokens"] += int(lens.sum())
+                d_sorted = f["d_sorted"]
+                perm = np.empty((m,), np.int64)
+                row0 = 0
+                for rows, S in self._batches(lens):
+                    B = len(rows)
+                    t0 = time.perf_counter()
+                    f["in_ev"][slot].synchronize()          # the batch that used this slot two launches ago is done
+                    t1 = time.perf_counter()
+                    h_ids = f["ids"][slot].numpy()[:B * S].reshape(B, S)
+                    h_lens = f["lens"][slot].numpy()[:B]
+                    self._pack(ids, lens, rows, S, h_ids, h_lens)
+                    stats["slot_wait_s"] += t1 - t0
+                    stats["pack_s"] += time.perf_counter() - t1
+                    dt = N.F32 | (0 if normalise else 0x100)
+                    N.check(N.lib().icd_encoder_forward(self._h, h_ids.ctypes.data, h_lens.ctypes.data, B, S,
+                                                        d_sorted[row0:row0 + B].data_ptr(), dt,
+                                                        C.c_void_p(stream.cuda_stream), 0), "icd_encoder_forward")
+                    f["in_ev"][slot].record(stream)
+                    stats["h2d_bytes"] += B * S * 4 + B * 4
+                    stats["batches"] += 1
+                    perm[row0:row0 + B] = rows
+                    row0 += B
+                    slot ^= 1
+                # un-sort on the device, copy back through the pinned slot of this chunk
+                if pending is not None and (pending[0] & 1) == (ci & 1):
+                    finish(pending)
+                    pending = None
+                inv = f["inv"][ci & 1].numpy()           # free again: chunk ci-2 was finished an iteration ago
+                inv[perm] = np.arange(m)
+                f["d_inv"][:m].copy_(f["inv"][ci & 1][:m], non_blocking=True)
+                f["out"][ci & 1][:m].copy_(d_sorted[:m].index_select(0, f["d_inv"][:m]), non_blocking=True)
+                f["out_ev"][ci & 1].record(stream)
+                if pending is not None:
+                    finish(pending)
+                pending = (ci, lo, hi)
+            if pending is not None:
+                finish(pending)
+        stats["total_s"] = time.perf_counter() - t_all
+        stats["tokenizer"] = self._tokenizer_kind()
+        self.last_stats = stats
+        return out
 
     def forward_ids(self, ids, lens, normalise: bool = True, out=None, stream: int = 0, sync: bool = True):
         """ids [B,S] int32, lens [B] int32 (numpy host or torch host/device) -> [B,hidden] float32."""
@@ -185,120 +331,3 @@ def load_tokenizer(path: str):
     except Exception:
         pass
     return bert_tokenizer_from_vocab(vocab_path)
-
-
-# ------------------------------------------------------------------------------------------
-def synthetic_engine(num_layers: int = 12, seed: int = 0, device: int = 0, vocab_size: int = 21128,
-                     max_tokens: int = 4096 * 64):
-    """Random-init encoder of the text2vec-base-chinese architecture (no checkpoint exists
-    offline): HF-style N(0, 0.02) init from a numpy generator.  Used by bench.py and smoke()."""
-    cfg = N.BertCfg(vocab_size=vocab_size, hidden=768, layers=num_layers, heads=12, intermediate=3072,
-                    max_position=512, type_vocab=2, ln_eps=1e-12)
-    n = int(N.lib().icd_encoder_weight_count(cfg))
-    rng = np.random.default_rng(seed)
-    blob = (rng.standard_normal(n, dtype=np.float32) * 0.02)
-    # LayerNorm gains must sit near 1: walk the canonical order and patch them
-    off = 0
-    H, I = 768, 3072
-    shapes = [vocab_size * H, 512 * H, 2 * H]
-    off = sum(shapes)
-    blob[off:off + H] = 1.0 + 0.1 * rng.standard_normal(H, dtype=np.float32); off += 2 * H
-    for _ in range(num_layers):
-        off += 3 * H * H + 3 * H + H * H + H
-        blob[off:off + H] = 1.0 + 0.1 * rng.standard_normal(H, dtype=np.float32); off += 2 * H
-        off += I * H + I + H * I + H
-        blob[off:off + H] = 1.0 + 0.1 * rng.standard_normal(H, dtype=np.float32); off += 2 * H
-    assert off == n
-    class _NoTok:
-        def __call__(self, *a, **k):
-            raise RuntimeError("synthetic engine has no tokenizer; use forward_ids")
-    return EncoderEngine(cfg=cfg, blob=blob, tokenizer=_NoTok(), device=device, max_tokens=max_tokens)
-
-
-def smoke() -> None:
-    """One tiny forward on cuda:0 against the CPU oracle (HF BertModel fp32)."""
-    import torch
-    from oracle import encoder as oenc
-    state = oenc.synthetic_state_dict(seed=3, num_layers=2, vocab_size=1000, max_position=512)
-    cfg = N.BertCfg(vocab_size=1000, hidden=768, layers=2, heads=12, intermediate=3072, max_position=512,
-                    type_vocab=2, ln_eps=1e-12)
-    blob = W.pack_state_dict(state, cfg)
-    eng = EncoderEngine(cfg=cfg, blob=blob, tokenizer=object(), device=0, max_tokens=4096)
-    rng = np.random.default_rng(0)
-    B, S = 6, 24
-    lens = np.array([24, 20, 13, 7, 2, 24], np.int32)
-    ids = np.zeros((B, S), np.int32)
-    for b in range(B):
-        ids[b, :lens[b]] = rng.integers(1, 1000, size=lens[b])
-    got = eng.forward_ids(ids, lens)
-    from transformers import BertModel
-    model = BertModel(oenc.bert_config(2, 1000, 512), add_pooling_layer=False)
-    model.load_state_dict(state, strict=False)
-    model.eval()
-    mask = torch.from_numpy((np.arange(S)[None, :] < lens[:, None]).astype(np.int64))
-    with torch.no_grad():
-        h = model(input_ids=torch.from_numpy(ids.astype(np.int64)), attention_mask=mask).last_hidden_state
-        m = mask.unsqueeze(-1).float()
-        ref = torch.nn.functional.normalize((h * m).sum(1) / m.sum(1).clamp(min=1e-9), dim=1).numpy()
-    cos = (got * ref).sum(1)
-    assert cos.min() >= 0.999, cos
-    eng.close()
-
-
-def bench_encoder(dev, peaks, batch: int = 4096, seq: int = 64, steps: int = 10, warmup: int = 3, barrier=None):
-    """BASELINE configs[2]: encoder throughput at S=64, B=4096 on synthetic ids, random-init
-    weights of the text2vec-base-chinese architecture.  Returns the `encoder` object of bench.py:
-    `value` with ids and outputs resident in HBM, `e2e` through icd_encoder_forward with pinned HOST ids /
-    lens / output (copies inside the timed region)."""
-    import torch
-    eng = synthetic_engine(device=dev.index or 0, max_tokens=batch * seq)
-    g = torch.Generator(device=dev).manual_seed(7)
-    ids = torch.randint(1000, 21128, (batch, seq), generator=g, device=dev, dtype=torch.int32)
-    ids[:, 0] = 101
-    ids[:, -1] = 102
-    lens = torch.full((batch,), seq, dtype=torch.int32, device=dev)
-    out = torch.empty((batch, 768), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream(dev)
-    launches0 = N.lib().icd_launch_count()
-    eng.forward_ids(ids, lens, out=out, stream=stream.cuda_stream, sync=False)
-    launches = int(N.lib().icd_launch_count() - launches0)
-    for _ in range(warmup):
-        eng.forward_ids(ids, lens, out=out, stream=stream.cuda_stream, sync=False)
-    torch.cuda.synchronize(dev)
-    if barrier is not None:
-        barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        eng.forward_ids(ids, lens, out=out, stream=stream.cuda_stream, sync=False)
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    if barrier is not None:
-        barrier()
-    ms = e0.elapsed_time(e1) / steps
-    # end to end: host token ids in, host embeddings out, every step
-    h_ids, h_lens = ids.cpu().pin_memory(), lens.cpu().pin_memory()
-    h_out = torch.empty((batch, 768), dtype=torch.float32).pin_memory()
-    eng.forward_ids(h_ids, h_lens, out=h_out, stream=stream.cuda_stream, sync=True)
-    e0.record(stream)
-    for _ in range(steps):
-        eng.forward_ids(h_ids, h_lens, out=h_out, stream=stream.cuda_stream, sync=True)
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    ms_e2e = e0.elapsed_time(e1) / steps
-    same = bool(torch.allclose(h_out, out.cpu(), atol=1e-6))
-    flops = batch * seq * 12 * (2 * (4 * 768 * 768 + 2 * 768 * 3072) + 4 * seq * 768)
-    tf = flops / (ms * 1e-3) / 1e12
-    norm = float(out.norm(dim=1).mean())
-    eng.close()
-    return {"metric": "text2vec sentences/sec", "value": batch / (ms * 1e-3), "unit": "sentences/s",
-            "ms_per_batch": ms, "steps": steps, "warmup": warmup, "flops_per_batch": flops, "batch": batch,
-            "seq_len": seq, "layers": 12, "dtype": "bf16",
-            "tflops": tf, "frac_of_bf16_sustained": tf / peaks["bf16_tflops_sustained"], "mean_norm": norm,
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "kernel": "gemm_tc_kernel (4 of the 5 launches per layer)", "peak_source": peaks["source"] + " (sustained)"},
-            "e2e": {"value": batch / (ms_e2e * 1e-3), "unit": "sentences/s", "h2d_bytes_per_step": batch * seq * 4 + batch * 4,
-                    "d2h_bytes_per_step": batch * 768 * 4, "host_equals_device": same},
-            "gpu_launches_per_batch": launches,
-            "data": "synthetic ids, random-init weights"}
