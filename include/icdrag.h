@@ -81,7 +81,9 @@ int icd_device_count(void);
  * "scan_kbs_pair" (K blocks per pipeline stage for single CTAs / CTA pairs, upper bounds: default 3 / 6),
  * "scan_pair" (CTA pairs: -1 auto, 0 off), "scan_qsplit" (last third of the query tile's K in shared
  * memory so that two accumulator buffers fit: -1 auto, 0 off), "scan_qtmem" (K blocks kept in TMEM when
- * split, 0 = all that fit).  Results never depend on them. */
+ * split, 0 = all that fit), "scan_generic" (1 = the run-time-shaped MMA issue loop instead of the unrolled one).
+ * Results never depend on them.  Production builds read NO environment variables on the compute path; profiling
+ * builds (-DICD_PROFILING) additionally honour ICD_SCAN_*, ICD_GEMM_PAIR, ICD_ENC_FUSED_LN, ICD_ATTN_DBG. */
 int icd_tune(const char* key, int value);
 
 /* ---------------------------------------------------------------- vector table + scan ------
@@ -170,9 +172,10 @@ int icd_encoder_destroy(icd_encoder* enc);
 int icd_encoder_reserve(icd_encoder* enc, int max_tokens);
 int icd_encoder_forward(icd_encoder* enc, const int32_t* ids, const int32_t* lens, int B, int S,
                         void* out, int out_dtype, void* stream, int sync);
-/* debug/parity hook: copy the hidden states after `layer` (0 = embeddings+LN, L = last) as
- * fp32 [B*S, hidden] of the last forward to a host/device buffer. */
-int icd_encoder_read_hidden(icd_encoder* enc, int layer_unused, float* out, int64_t count);
+/* parity hook: copy the LAST layer's hidden states (after its closing LayerNorm) of the last forward as fp32
+ * [B*S, hidden] to a host/device buffer.  `reserved` must be 0 (intermediate layers are not kept: their streams are
+ * overwritten in place). */
+int icd_encoder_read_hidden(icd_encoder* enc, int reserved, float* out, int64_t count);
 
 /* Token-classification head on the same encoder: the per-token logits that
  * AutoModelForTokenClassification produces inside the reference's NER pipeline

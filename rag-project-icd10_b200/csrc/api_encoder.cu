@@ -223,11 +223,13 @@ int icd_encoder_create(const float* weights, int64_t count, const icd_bert_cfg* 
   take((int64_t)cfg->type_vocab * H, false, (void**)&e->type);
   take(H, false, (void**)&e->eg);
   take(H, false, (void**)&e->eb);
-  // ICD_ENC_FUSED_LN=0 keeps the separate LayerNorm launches (A/B timing); the weights are prepared for one mode
+#ifdef ICD_PROFILING
+  // profiling builds only: ICD_ENC_FUSED_LN=0 keeps the separate LayerNorm launches (A/B timing)
   {
     const char* v = getenv("ICD_ENC_FUSED_LN");
     e->fused_ln = !(v && *v && atoi(v) == 0);
   }
+#endif
   const float *prev_g = nullptr, *prev_b = nullptr;  // host: the LayerNorm that closes the previous layer
   std::vector<float> wf, bf, cf, sum;
   auto upload_vec = [&](const std::vector<float>& v, float** dst) {
@@ -358,12 +360,10 @@ static int encode_hidden(icd_encoder* e, const int32_t* ids, const int32_t* lens
     ICD_CUDA(cudaMemcpyAsync(e->lens, lens, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     d_lens = e->lens;
   }
-  static const bool cuda_core_attention = getenv("ICD_ATTN_CUDA_CORE") != nullptr;  // A/B timing only
-  ICD_TRY(launch_embed_ln(d_ids, M, S, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
-  auto attention = [&]() {
-    return cuda_core_attention ? launch_attention(e->qkv, d_lens, B, S, e->ctx, st)
-                               : launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st);
-  };
+  // ids outside the embedding table read [UNK] (100 in BERT vocabularies) instead of faulting
+  const int unk = e->cfg.vocab_size > 100 ? 100 : 0;
+  ICD_TRY(launch_embed_ln(d_ids, M, S, e->cfg.vocab_size, unk, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
+  auto attention = [&]() { return launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st); };
   const void* final_h = e->h;
   if (e->fused_ln) {
     // Deferred LayerNorm: e->h carries the layer input -- normalised for layer 0 (embed_ln), the un-normalised
@@ -523,8 +523,8 @@ int icd_encoder_token_logits(icd_encoder* e, const int32_t* ids, const int32_t* 
   return ICD_OK;
 }
 
-int icd_encoder_read_hidden(icd_encoder* e, int layer_unused, float* out, int64_t count) {
-  (void)layer_unused;
+int icd_encoder_read_hidden(icd_encoder* e, int reserved, float* out, int64_t count) {
+  (void)reserved;
   ICD_CHECK_ARG(e && out, "null argument");
   ICD_CHECK_ARG(count == (int64_t)e->last_M * e->cfg.hidden, "count must be tokens*hidden of the last forward");
   ICD_CUDA(cudaSetDevice(e->device));

@@ -54,7 +54,9 @@ constexpr int kSmemBytes = kSlots * kSlotBytes + 2 * kTileBytes /*ctx staging, o
 struct AttParams {
   const int32_t* lens;
   int B, S, G, tiles;
-  int dbg;  // ICD_ATTN_DBG (profiling only): 1 = skip the ctx stores, 2 = every item loads tile 0 (L2 hits)
+#ifdef ICD_PROFILING
+  int dbg;  // ICD_ATTN_DBG (profiling builds only): 1 = skip the ctx stores, 2 = every item loads tile 0 (L2 hits)
+#endif
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -119,7 +121,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       for (int j = 0; j < n_local; ++j) {
         const int item = (int)blockIdx.x + j * (int)gridDim.x;
         const int tile = item / kHeads, head = item % kHeads;
+#ifdef ICD_PROFILING
         const int row0 = (p.dbg & 2) ? 0 : tile * p.G * p.S;
+#else
+        const int row0 = tile * p.G * p.S;
+#endif
         const int slot = j % kSlots;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), ((j / kSlots) & 1) ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
@@ -211,7 +217,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       }
       ptx::fence_proxy_async_smem();
       wg_sync();
+#ifdef ICD_PROFILING
       if (leader && !(p.dbg & 1)) {
+#else
+      if (leader) {
+#endif
         // the box is G * S rows tall (the rows this tile owns); rows past the end of the buffer are clipped
         ptx::tma_store_2d(&tmap_ctx, stage_u32, head * HD, row0);
         ptx::tma_store_commit();
@@ -357,10 +367,12 @@ int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S,
   p.S = S;
   p.G = kTile / S;
   p.tiles = (B + p.G - 1) / p.G;
+#ifdef ICD_PROFILING
   {
     static const int dbg = getenv("ICD_ATTN_DBG") ? atoi(getenv("ICD_ATTN_DBG")) : 0;
     p.dbg = dbg;
   }
+#endif
   CUtensorMap tm;
   memcpy(&tm, tmap_qkv, sizeof(tm));
   // ctx store box: the G * S rows a tile owns x one head (64 columns); encoded per launch because it depends on S

@@ -53,13 +53,14 @@ __device__ __forceinline__ void ln_store(const float* x, const float* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-embed_ln_kernel(const int32_t* __restrict__ ids, int M, int S, const float* __restrict__ word,
+embed_ln_kernel(const int32_t* __restrict__ ids, int M, int S, int vocab, int unk, const float* __restrict__ word,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * 8 + warp;
   if (tok >= M) return;
-  const int id = ids[tok];
+  int id = ids[tok];
+  if ((unsigned)id >= (unsigned)vocab) id = unk;  // an id outside the table (mismatched vocab.txt) reads [UNK], not foreign memory
   const int t = tok % S;
   float x[kPerLane];
 #pragma unroll
@@ -99,98 +100,6 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int M, const float* __res
     x[c * 8 + 7] = bf16hi_to_f32(v.w);
   }
   ln_store(x, gamma, beta, eps, out + (size_t)tok * H, lane);
-}
-
-// ---------------------------------------------------------------- attention (S <= 128)
-// One CTA per (sequence, head); thread t owns query row t and runs an online softmax over the
-// keys j < len.  K and V of the head sit in shared memory as fp32 (broadcast reads).
-constexpr int HD = 64;
-__global__ void __launch_bounds__(128)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
-                 __nv_bfloat16* __restrict__ ctx) {
-  extern __shared__ __align__(16) float sm[];
-  float* Ks = sm;            // [S][64]
-  float* Vs = sm + S * HD;   // [S][64]
-  const int b = blockIdx.x, h = blockIdx.y;
-  const int len = min(lens[b], S);
-  const size_t row0 = (size_t)b * S;
-  // cooperative load of K, V rows j < len (8 bf16 per thread per step)
-  for (int i = threadIdx.x; i < len * (HD / 8); i += blockDim.x) {
-    const int j = i / (HD / 8), c = (i % (HD / 8)) * 8;
-    const __nv_bfloat16* base = qkv + (row0 + j) * (3 * H) + h * HD + c;
-    const uint4 kv = *reinterpret_cast<const uint4*>(base + H);
-    const uint4 vv = *reinterpret_cast<const uint4*>(base + 2 * H);
-    float* kd = Ks + j * HD + c;
-    float* vd = Vs + j * HD + c;
-    kd[0] = bf16lo_to_f32(kv.x); kd[1] = bf16hi_to_f32(kv.x); kd[2] = bf16lo_to_f32(kv.y); kd[3] = bf16hi_to_f32(kv.y);
-    kd[4] = bf16lo_to_f32(kv.z); kd[5] = bf16hi_to_f32(kv.z); kd[6] = bf16lo_to_f32(kv.w); kd[7] = bf16hi_to_f32(kv.w);
-    vd[0] = bf16lo_to_f32(vv.x); vd[1] = bf16hi_to_f32(vv.x); vd[2] = bf16lo_to_f32(vv.y); vd[3] = bf16hi_to_f32(vv.y);
-    vd[4] = bf16lo_to_f32(vv.z); vd[5] = bf16hi_to_f32(vv.z); vd[6] = bf16lo_to_f32(vv.w); vd[7] = bf16hi_to_f32(vv.w);
-  }
-  __syncthreads();
-  const int t = threadIdx.x;
-  if (t >= S) return;
-  __nv_bfloat16* orow = ctx + (row0 + t) * H + h * HD;
-  if (t >= len) {  // padded query rows are never read downstream (masked keys, masked pooling)
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  float q[HD];
-  {
-    const __nv_bfloat16* qb = qkv + (row0 + t) * (3 * H) + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      const uint4 v = *reinterpret_cast<const uint4*>(qb + c * 8);
-      // fold the 1/sqrt(64) scale and log2(e) into q: softmax runs in base 2
-      const float sc = 0.125f * 1.4426950408889634f;
-      q[c * 8 + 0] = bf16lo_to_f32(v.x) * sc; q[c * 8 + 1] = bf16hi_to_f32(v.x) * sc;
-      q[c * 8 + 2] = bf16lo_to_f32(v.y) * sc; q[c * 8 + 3] = bf16hi_to_f32(v.y) * sc;
-      q[c * 8 + 4] = bf16lo_to_f32(v.z) * sc; q[c * 8 + 5] = bf16hi_to_f32(v.z) * sc;
-      q[c * 8 + 6] = bf16lo_to_f32(v.w) * sc; q[c * 8 + 7] = bf16hi_to_f32(v.w) * sc;
-    }
-  }
-  float acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int j = 0; j < len; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD);
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int c = 0; c < HD / 4; c += 2) {
-      const float4 k0 = kr[c], k1 = kr[c + 1];
-      s0 = fmaf(q[4 * c + 0], k0.x, s0); s0 = fmaf(q[4 * c + 1], k0.y, s0);
-      s0 = fmaf(q[4 * c + 2], k0.z, s0); s0 = fmaf(q[4 * c + 3], k0.w, s0);
-      s1 = fmaf(q[4 * c + 4], k1.x, s1); s1 = fmaf(q[4 * c + 5], k1.y, s1);
-      s1 = fmaf(q[4 * c + 6], k1.z, s1); s1 = fmaf(q[4 * c + 7], k1.w, s1);
-    }
-    const float s = s0 + s1;
-    const float mn = fmaxf(m, s);
-    const float corr = exp2f(m - mn);  // 0 on the first key (m = -inf)
-    const float pj = exp2f(s - mn);
-    l = fmaf(l, corr, pj);
-    m = mn;
-    const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD);
-#pragma unroll
-    for (int c = 0; c < HD / 4; ++c) {
-      const float4 v = vr[c];
-      acc[4 * c + 0] = fmaf(acc[4 * c + 0], corr, pj * v.x);
-      acc[4 * c + 1] = fmaf(acc[4 * c + 1], corr, pj * v.y);
-      acc[4 * c + 2] = fmaf(acc[4 * c + 2], corr, pj * v.z);
-      acc[4 * c + 3] = fmaf(acc[4 * c + 3], corr, pj * v.w);
-    }
-  }
-  const float inv = 1.0f / l;
-#pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    uint4 o;
-    o.x = pack2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
-    o.y = pack2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
-    o.z = pack2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
-    o.w = pack2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
-    *reinterpret_cast<uint4*>(orow + c * 8) = o;
-  }
 }
 
 // ---------------------------------------------------------------- masked mean + L2 normalise
@@ -267,9 +176,9 @@ int launch_token_head(const void* h, int M, const float* w, const float* b, int 
   return ICD_OK;
 }
 
-int launch_embed_ln(const int32_t* ids, int M, int S, const float* word, const float* pos, const float* type0,
-                    const float* gamma, const float* beta, float eps, void* out, cudaStream_t st) {
-  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, M, S, word, pos, type0, gamma, beta, eps,
+int launch_embed_ln(const int32_t* ids, int M, int S, int vocab, int unk, const float* word, const float* pos,
+                    const float* type0, const float* gamma, const float* beta, float eps, void* out, cudaStream_t st) {
+  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, M, S, vocab, unk, word, pos, type0, gamma, beta, eps,
                                               reinterpret_cast<__nv_bfloat16*>(out));
   count_launch();
   ICD_CUDA(cudaGetLastError());
@@ -280,21 +189,6 @@ int launch_layernorm(const void* x, int M, const float* gamma, const float* beta
                      cudaStream_t st) {
   layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, gamma, beta, eps,
                                                reinterpret_cast<__nv_bfloat16*>(out));
-  count_launch();
-  ICD_CUDA(cudaGetLastError());
-  return ICD_OK;
-}
-
-int launch_attention(const void* qkv, const int32_t* lens, int B, int S, void* ctx, cudaStream_t st) {
-  if (S > 128) {
-    set_error("attention: S=%d > 128", S);
-    return ICD_E_UNSUPPORTED;
-  }
-  const size_t smem = (size_t)2 * S * HD * 4;
-  ICD_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * HD * 4));
-  const int threads = ((S + 31) / 32) * 32;
-  attention_kernel<<<dim3(B, 12), threads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), lens, S,
-                                                      reinterpret_cast<__nv_bfloat16*>(ctx));
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;

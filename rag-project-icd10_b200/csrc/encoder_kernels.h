@@ -31,15 +31,14 @@ int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K);
 int gemm_make_map_out(void* map128, const void* base, int64_t rows, int N);
 
 // ---- encoder_kernels.cu
-// h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0])
-int launch_embed_ln(const int32_t* ids, int M, int S, const float* word, const float* pos, const float* type0,
-                    const float* gamma, const float* beta, float eps, void* out_bf16, cudaStream_t st);
+// h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0]); ids outside [0, vocab) read row `unk`
+int launch_embed_ln(const int32_t* ids, int M, int S, int vocab, int unk, const float* word, const float* pos,
+                    const float* type0, const float* gamma, const float* beta, float eps, void* out_bf16, cudaStream_t st);
 // out = LayerNorm(x) row-wise over 768 columns
 int launch_layernorm(const void* x_bf16, int M, const float* gamma, const float* beta, float eps, void* out_bf16,
                      cudaStream_t st);
-// softmax(Q K^T / 8 + mask) V for every (sequence, head); qkv is [M, 2304] = [q | k | v]
-int launch_attention(const void* qkv_bf16, const int32_t* lens, int B, int S, void* ctx_bf16, cudaStream_t st);
-// attention_tc.cu: the same on tensor cores (tcgen05); tmap_qkv from attention_make_map over the [rows, 2304] buffer
+// attention_tc.cu: softmax(Q K^T / 8 + mask) V for every (sequence, head) on tensor cores (tcgen05); qkv is
+// [M, 2304] = [q | k | v]; tmap_qkv from attention_make_map over the [rows, 2304] buffer
 int attention_make_map(void* map128, const void* qkv_bf16, int64_t rows);
 // ctx_rows = rows of the ctx buffer (a multiple of 128 >= B*S): the store boxes are clipped against it
 int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx_bf16, int64_t ctx_rows,

@@ -440,14 +440,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 int gemm_tile_n() { return BN; }
 
-// CTA pairs by default; ICD_GEMM_PAIR=0 selects the single-CTA kernel (A/B timing, and the fallback when the
-// device cannot co-schedule clusters of 2)
+// CTA pairs; profiling builds can select the single-CTA kernel with ICD_GEMM_PAIR=0 (A/B timing)
 static int pair_mode() {
+#ifdef ICD_PROFILING
   static const int mode = [] {
     const char* v = getenv("ICD_GEMM_PAIR");
     return (v && *v) ? (atoi(v) != 0 ? 2 : 1) : 2;
   }();
   return mode;
+#else
+  return 2;
+#endif
 }
 
 template <int NC, int EPI, bool LNIN, bool STATS>

@@ -526,12 +526,17 @@ int make_tmap_bf16_3d(void* map128, const void* base, uint64_t d0, uint64_t d1, 
   return ICD_OK;
 }
 
-// tuning knobs: defaults from the environment (ICD_SCAN_BN = 64 | 128, ICD_SCAN_DRIFT = tiles, 0 = limiter
+// tuning knobs: defaults (profiling builds, -DICD_PROFILING: from the environment -- ICD_SCAN_BN = 64 | 128, ICD_SCAN_DRIFT = tiles, 0 = limiter
 // off, ICD_SCAN_TMAX = query tiles sharing one row stream per launch, ICD_SCAN_KBS = K blocks per stage,
 // ICD_SCAN_SAMPLE = pre-pass stride, 0 = off, -1 = by table size); icd_tune() overrides them at run time.
 static int env_int(const char* name, int dflt) {
+#ifdef ICD_PROFILING
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+#else
+  (void)name;   // production builds ignore the environment: knobs move only through icd_tune()
+  return dflt;
+#endif
 }
 struct Tunables {
   int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, gen;

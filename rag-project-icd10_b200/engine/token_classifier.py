@@ -113,7 +113,7 @@ class TokenClassifierEngine:
                  head_bias: Optional[np.ndarray] = None, id2label: Optional[Dict[int, str]] = None,
                  tokenizer=None, max_tokens: int = 1024 * 128, stride: int = 16, horizon: int = 512):
         if encoder is None:
-            path = W.resolve_model_dir(model_name_or_path)
+            path = W.resolve_model_dir(model_name_or_path, allow_env_override=False)
             cfg, blob, _meta = W.load_model_dir(path)
             state = W.load_state(path)
             head_weight = np.asarray(state["classifier.weight"], np.float32)

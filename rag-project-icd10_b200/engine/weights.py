@@ -16,7 +16,10 @@ from .. import _native as N
 
 def config_from_dict(cfg: dict) -> N.BertCfg:
     if cfg.get("model_type", "bert") != "bert":
-        raise ValueError(f"only BERT encoders are supported (model_type={cfg.get('model_type')})")
+        raise ValueError(f"only BERT-base encoders are supported (model_type={cfg.get('model_type')}); the supported "
+                         "embedding model is shibing624/text2vec-base-chinese (EMBEDDING_MODEL_NAME in the reference's "
+                         "env.example) -- the reference's code default intfloat/multilingual-e5-large-instruct is XLM-R "
+                         "large and is not served by this engine")
     if cfg.get("hidden_act", "gelu") != "gelu":
         raise ValueError("only erf-GELU ('gelu') is supported")
     if cfg.get("position_embedding_type", "absolute") != "absolute":
@@ -60,9 +63,10 @@ def pack_state_dict(state: Dict[str, "np.ndarray"], cfg: N.BertCfg) -> np.ndarra
     return blob
 
 
-def resolve_model_dir(name_or_path: str) -> str:
-    """A directory, $ICD_B200_MODEL_DIR, or an entry of the local HF cache (no network)."""
-    env = os.environ.get("ICD_B200_MODEL_DIR")
+def resolve_model_dir(name_or_path: str, allow_env_override: bool = True) -> str:
+    """A directory, $ICD_B200_MODEL_DIR (the EMBEDDING model's directory: callers loading any other model pass
+    allow_env_override=False), or an entry of the local HF cache (no network)."""
+    env = os.environ.get("ICD_B200_MODEL_DIR") if allow_env_override else None
     for cand in (name_or_path, env):
         if cand and os.path.isdir(cand) and os.path.exists(os.path.join(cand, "config.json")):
             return cand
@@ -91,11 +95,28 @@ def load_model_dir(path: str) -> Tuple[N.BertCfg, np.ndarray, dict]:
         cfg_d = json.load(fh)
     cfg = config_from_dict(cfg_d)
     state = load_state(path)
-    meta = {"max_seq_length": 128, "do_lower_case_text": False}
+    meta = {"max_seq_length": 128, "do_lower_case_text": False, "pooling": "mean"}
     sb = os.path.join(path, "sentence_bert_config.json")
     if os.path.exists(sb):
         with open(sb, encoding="utf-8") as fh:
             d = json.load(fh)
         meta["max_seq_length"] = int(d.get("max_seq_length", 128))
         meta["do_lower_case_text"] = bool(d.get("do_lower_case", False))
+    # sentence-transformers pooling module (1_Pooling/config.json): this engine implements masked MEAN pooling only
+    # (text2vec-base-chinese); a CLS- or max-pooled model would silently produce different embeddings
+    pool = os.path.join(path, "1_Pooling", "config.json")
+    if os.path.exists(pool):
+        with open(pool, encoding="utf-8") as fh:
+            pc = json.load(fh)
+        modes = [k for k, v in pc.items() if k.startswith("pooling_mode_") and v is True]
+        if modes != ["pooling_mode_mean_tokens"]:
+            raise ValueError(f"{path}: pooling modes {modes} are not supported (masked mean pooling only, as in "
+                             "shibing624/text2vec-base-chinese)")
+    if meta["do_lower_case_text"]:
+        raise ValueError(f"{path}: sentence_bert_config.json asks for text lower-casing before tokenisation, which this "
+                         "engine does not apply")
+    if meta["max_seq_length"] > 128:
+        import warnings
+        warnings.warn(f"{path}: max_seq_length {meta['max_seq_length']} exceeds this engine's 128-token kernel limit; "
+                      "inputs are truncated at 128 tokens (text2vec-base-chinese uses 128)", RuntimeWarning, stacklevel=2)
     return cfg, pack_state_dict(state, cfg), meta
