@@ -57,12 +57,17 @@ class EncoderEngine:
         return int(self.cfg.hidden)
 
     def encode(self, sentences, batch_size: int = 32, show_progress_bar=None, normalize_embeddings: bool = False,
-               convert_to_numpy: bool = True, **_ignored):
+               convert_to_numpy: bool = True, convert_to_tensor: bool = False, **_ignored):
+        """convert_to_tensor=True (SentenceTransformer's switch) returns a float32 CUDA tensor: the embeddings stay on
+        the device they were computed on (the sharded build appends them to that GPU's table without a host round trip)."""
         single = isinstance(sentences, str)
         items: List[str] = [sentences] if single else list(sentences)
         if not items:
+            if convert_to_tensor:
+                import torch
+                return torch.zeros((0, self.cfg.hidden), dtype=torch.float32, device=torch.device("cuda", self.device_index))
             return np.zeros((0, self.cfg.hidden), np.float32)
-        out = self._encode_texts(items, normalize_embeddings)
+        out = self._encode_texts(items, normalize_embeddings, to_device=convert_to_tensor)
         return out[0] if single else out
 
     def close(self) -> None:
@@ -117,9 +122,9 @@ class EncoderEngine:
             yield order[lo:lo + B], S
             lo += B
 
-    def _encode_texts(self, items: List[str], normalise: bool) -> np.ndarray:
+    def _encode_texts(self, items: List[str], normalise: bool, to_device: bool = False):
         n, H = len(items), int(self.cfg.hidden)
-        if n <= SMALL_BATCH:
+        if n <= SMALL_BATCH and not to_device:
             # direct path (the reference's live pattern is batch 1): one tokeniser call, synchronous launches
             t0 = time.perf_counter()
             ids, lens = self._token_table(items)
@@ -134,7 +139,7 @@ class EncoderEngine:
                                "encode_s": time.perf_counter() - t1, "h2d_bytes": int(lens.sum()) * 4,
                                "tokenizer": self._tokenizer_kind()}
             return out
-        return self._encode_pipelined(items, normalise)
+        return self._encode_pipelined(items, normalise, to_device)
 
     def _tokenizer_kind(self) -> str:
         if self._ntok is not None and self._ntok.native:
@@ -160,7 +165,7 @@ class EncoderEngine:
             self._feed = f
         return self._feed
 
-    def _encode_pipelined(self, items: List[str], normalise: bool) -> np.ndarray:
+    def _encode_pipelined(self, items: List[str], normalise: bool, to_device: bool = False):
         """The feeder (SURVEY section 7 "hard part"): while the GPU encodes chunk c, a worker thread tokenises chunk
         c+1 (the C call releases the GIL) and the main thread packs length-bucketed batches into pinned slots; every
         launch is asynchronous on one stream, embeddings land in sorted order on the device, are un-sorted there and
@@ -168,7 +173,8 @@ class EncoderEngine:
         import torch
         f = self._feed_buffers()
         n, H = len(items), int(self.cfg.hidden)
-        out = np.empty((n, H), np.float32)
+        out = None if to_device else np.empty((n, H), np.float32)
+        out_dev = torch.empty((n, H), dtype=torch.float32, device=f["dev"]) if to_device else None
         stream = f["stream"]
         chunks = [(lo, min(n, lo + FEED_CHUNK)) for lo in range(0, n, FEED_CHUNK)]
         stats = {"sentences": n, "tokens": 0, "h2d_bytes": 0, "tokenize_wait_s": 0.0, "pack_s": 0.0, "slot_wait_s": 0.0,
@@ -224,6 +230,12 @@ class EncoderEngine:
                 inv = f["inv"][ci & 1].numpy()           # free again: chunk ci-2 was finished an iteration ago
                 inv[perm] = np.arange(m)
                 f["d_inv"][:m].copy_(f["inv"][ci & 1][:m], non_blocking=True)
+                if to_device:
+                    torch.index_select(d_sorted[:m], 0, f["d_inv"][:m], out=out_dev[lo:hi])
+                    f["out_ev"][ci & 1].record(stream)      # the pinned `inv` slot is free once this has run
+                    if ci >= 1:
+                        f["out_ev"][(ci - 1) & 1].synchronize()
+                    continue
                 f["out"][ci & 1][:m].copy_(d_sorted[:m].index_select(0, f["d_inv"][:m]), non_blocking=True)
                 f["out_ev"][ci & 1].record(stream)
                 if pending is not None:
@@ -231,10 +243,12 @@ class EncoderEngine:
                 pending = (ci, lo, hi)
             if pending is not None:
                 finish(pending)
+            if to_device:
+                stream.synchronize()
         stats["total_s"] = time.perf_counter() - t_all
         stats["tokenizer"] = self._tokenizer_kind()
         self.last_stats = stats
-        return out
+        return out_dev if to_device else out
 
     def forward_ids(self, ids, lens, normalise: bool = True, out=None, stream: int = 0, sync: bool = True):
         """ids [B,S] int32, lens [B] int32 (numpy host or torch host/device) -> [B,hidden] float32."""

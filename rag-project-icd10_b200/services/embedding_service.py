@@ -111,6 +111,12 @@ class EmbeddingService:
             raise RuntimeError("嵌入模型未加载")
         return self.model.encode([f"query: {q}" for q in queries], normalize_embeddings=True)
 
+    # extension for the sharded build: the embeddings stay on this rank's GPU (a float32 CUDA tensor)
+    def encode_queries_device(self, queries: List[str]):
+        if not self.model:
+            raise RuntimeError("嵌入模型未加载")
+        return self.model.encode([f"query: {q}" for q in queries], normalize_embeddings=True, convert_to_tensor=True)
+
     def get_model_info(self) -> Dict[str, Any]:
         if not self.model:
             return {"loaded": False}

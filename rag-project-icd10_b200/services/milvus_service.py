@@ -24,12 +24,61 @@ from ..engine.store import DataType, IcdStoreClient
 
 MilvusClient = IcdStoreClient  # the name the reference constructs (milvus_service.py:81,110)
 
+
+class LazyCandidates:
+    """What MilvusService.search returns for one query -- a list of candidate dicts in the reference's order -- with
+    the dicts built on access.  Compares equal to the list; ``list(x)`` materialises it."""
+
+    def __init__(self, service, raw, ids):
+        keep = ids >= 0
+        self._svc, self._raw, self._ids = service, raw[keep], ids[keep]
+        self._cache: Dict[int, Dict[str, Any]] = {}
+
+    def __len__(self) -> int:
+        return int(self._ids.shape[0])
+
+    def _one(self, i: int) -> Dict[str, Any]:
+        if i not in self._cache:
+            self._cache[i] = self._svc._candidate_of_row(int(self._ids[i]), float(self._raw[i]))
+        return self._cache[i]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._one(j) for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return self._one(i)
+
+    def __iter__(self):
+        return (self._one(i) for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self) -> str:
+        return repr(list(self))
+
+    @property
+    def row_ids(self):
+        return self._ids
+
+    @property
+    def raw_scores(self):
+        return self._raw
+
 _OUTPUT_FIELDS = ["code", "preferred_zh", "has_complication", "main_code", "secondary_code", "level",
                   "parent_code", "category_path", "semantic_text"]
 _LEVEL_WEIGHTS = {1: 1.2, 2: 1.0, 3: 0.8}  # reference :550-558
 
 
 class MilvusService:
+    # extra keyword arguments for the store client: device=<gpu index>, shard=(rank, world) when one process per GPU
+    # serves a row shard each (set by tools/build_database.py under torchrun); empty for the reference's single process
+    client_kwargs: Dict[str, Any] = {}
+
     def __init__(self, embedding_service=None):
         self.config = self._load_config()
         self.collection_name = self.config.get("milvus", {}).get("collection_name", "icd10")
@@ -84,7 +133,7 @@ class MilvusService:
                 if db_dir and not os.path.exists(db_dir):
                     os.makedirs(db_dir, exist_ok=True)
                     logger.info(f"创建数据库目录: {db_dir}")
-                self.client = MilvusClient(uri=db_path)
+                self.client = MilvusClient(uri=db_path, **type(self).client_kwargs)
                 logger.info(f"成功连接到本地向量库: {db_path}")
             elif mode == "remote":
                 # a remote Milvus server is outside this engine: the table lives in this process's HBM
@@ -224,25 +273,74 @@ class MilvusService:
             },
         }
 
-    # extension: all diagnoses of a request in one scan launch; each element is
-    # exactly what search() returns for that vector
-    def search_batch(self, query_vectors, top_k: int = 10) -> List[List[Dict[str, Any]]]:
+    # extension: all diagnoses of a request in ONE scan launch, level re-rank on the GPU
+    # (ICD_WEIGHT_RERANK == the sort at :314).  Element b is what search(query_vectors[b], top_k) returns; the hit
+    # dicts are built lazily, on access, from the mapped columns -- 10 000 queries do not cost 100 000 dicts up front.
+    def search_batch(self, query_vectors, top_k: int = 10) -> List["LazyCandidates"]:
         try:
             if not self.client.has_collection(collection_name=self.collection_name):
                 logger.error(f"集合 {self.collection_name} 不存在")
                 return []
             q = np.asarray(query_vectors, dtype=np.float32)
-            results = self.client.search(collection_name=self.collection_name, data=q, limit=top_k,
-                                         output_fields=_OUTPUT_FIELDS)
-            out = []
-            for hits in results:
-                cands = [self._candidate(h) for h in hits]
-                cands.sort(key=lambda c: c["score"], reverse=True)
-                out.append(cands)
-            return out
+            if q.ndim == 1:
+                q = q[None, :]
+            _score, raw, ids = self.client.search_ranked(self.collection_name, q, top_k)
+            return [LazyCandidates(self, raw[b], ids[b]) for b in range(q.shape[0])]
         except Exception as e:
             logger.error(f"搜索失败: {e}")
             return []
+
+    def _candidate_of_row(self, row_id: int, distance: float) -> Dict[str, Any]:
+        """The candidate dict of one (row, raw inner product): same arithmetic as _candidate (Python floats)."""
+        f = lambda name: self.client.field(self.collection_name, name, row_id)   # noqa: E731
+        level = f("level")
+        base = float(distance)
+        return {
+            "code": f("code"),
+            "title": f("preferred_zh"),
+            "score": float(base * self._calculate_level_weight(level)),
+            "original_score": float(base),
+            "metadata": {
+                "has_complication": f("has_complication"),
+                "main_code": f("main_code"),
+                "secondary_code": f("secondary_code"),
+                "level": level,
+                "parent_code": f("parent_code"),
+                "category_path": f("category_path"),
+                "semantic_text": f("semantic_text"),
+            },
+        }
+
+    @staticmethod
+    def _row_of_record(rec: Dict[str, Any]) -> Dict[str, Any]:
+        """The scalar fields insert_records stores for one record (reference :233-244: None codes become '')."""
+        main_code, secondary = rec.get("main_code"), rec.get("secondary_code")
+        return {
+            "code": rec["code"],
+            "preferred_zh": rec.get("preferred_zh", ""),
+            "has_complication": rec.get("has_complication", False),
+            "main_code": "" if main_code is None else main_code,
+            "secondary_code": "" if secondary is None else secondary,
+            "level": rec.get("level", 1),
+            "parent_code": rec.get("parent_code", ""),
+            "category_path": rec.get("category_path", ""),
+            "semantic_text": rec.get("semantic_text", ""),
+        }
+
+    # extension (SURVEY 8e / 8a-P): the build path hands over one [n, dim] float32 array (numpy, or a torch tensor
+    # still on the GPU) instead of n Python lists; same validation and bool result as insert_records
+    def insert_records_array(self, records: List[Dict[str, Any]], vectors) -> bool:
+        if len(records) != int(vectors.shape[0]):
+            raise ValueError("记录数量与向量数量不匹配")
+        logger.info(f"准备插入 {len(records)} 条记录到集合 {self.collection_name}")
+        try:
+            rows = [self._row_of_record(rec) for rec in records]
+            self.client.insert_arrays(self.collection_name, rows, vectors)
+            logger.info(f"成功插入 {len(records)} 条记录")
+            return True
+        except Exception as e:
+            logger.error(f"插入记录失败: {e}")
+            return False
 
     # reference :322-342
     def get_collection_stats(self) -> Dict[str, Any]:

@@ -34,13 +34,16 @@ else:
     from ..services.embedding_service import EmbeddingService
     from ..services.milvus_service import MilvusService
 
-ENCODE_CHUNK = 8192  # records encoded per GPU call (a multiple of every insert batch size)
+ENCODE_CHUNK = 65536  # records encoded per GPU call (a multiple of every insert batch size): the whole ICD table in one pass
 
 
 class DatabaseBuilder:
-    def __init__(self):
+    def __init__(self, rank: int = 0, world: int = 1, dist=None):
+        """rank / world / dist: one process per GPU (torchrun); the default is the reference's single process."""
         self.embedding_service = None
         self.milvus_service = None
+        self.rank, self.world, self.dist = int(rank), int(world), dist
+        self.shard_group = None
         try:
             logger.add("logs/database_build.log", rotation="50 MB", level="INFO")
         except Exception:
@@ -50,6 +53,11 @@ class DatabaseBuilder:
     def initialize_services(self):
         logger.info("初始化服务...")
         try:
+            if self.world > 1:
+                # one encoder replica and one row shard of the table per GPU
+                local = int(os.environ.get("LOCAL_RANK", self.rank))
+                os.environ["EMBEDDING_DEVICE"] = f"cuda:{local}"
+                MilvusService.client_kwargs = {"device": local, "shard": (self.rank, self.world)}
             self.embedding_service = EmbeddingService()
             probe = self.embedding_service.test_embedding("测试")
             if not probe.get("success"):
@@ -147,9 +155,60 @@ class DatabaseBuilder:
             return 128
         return 256
 
+    def _barrier(self):
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier()
+
+    # SURVEY 8e (encoder row): the same build with the records split over the GPUs of one box.  Shard r encodes exactly
+    # the rows it will hold -- rows shard_rows(n, r, world), in CSV order, so global row ids equal the single-process
+    # build's -- appends them to ITS device table straight from the encoder's output buffer, and writes its slice of the
+    # flat column files; rank 0 writes the scalar columns and commits the header.  No collective on the data path.
+    def vectorize_and_index_sharded(self, records: List[Dict]) -> bool:
+        import importlib
+        import time
+        store = self.milvus_service.client
+        name = self.milvus_service.collection_name
+        shard = importlib.import_module(__package__.rsplit(".", 1)[0] + ".engine.shard" if __package__ else
+                                        "rag-project-icd10_b200.engine.shard")
+        lo, hi = shard.shard_bounds(len(records), self.rank, self.world)
+        stats = {"records": len(records), "rows_local": hi - lo, "encode_s": 0.0, "insert_s": 0.0, "load_s": 0.0}
+        self.last_build_stats = stats
+        try:
+            logger.info(f"分片向量化: rank {self.rank}/{self.world} 处理记录 [{lo}, {hi})")
+            if self.rank == 0:
+                rows_all = [self.milvus_service._row_of_record(r) for r in records]
+                store.sharded_append_prepare(name, rows_all)
+            self._barrier()
+            part = records[lo:hi]
+            t0 = time.perf_counter()
+            texts = [r.get("semantic_text", r.get("preferred_zh", "")) for r in part]
+            vectors = self.embedding_service.encode_queries_device(texts)       # stays on this GPU
+            t1 = time.perf_counter()
+            store.sharded_append_slice(name, lo, [self.milvus_service._row_of_record(r) for r in part], vectors)
+            stats["encode_s"], stats["insert_s"] = t1 - t0, time.perf_counter() - t1
+            self._barrier()
+            if self.rank == 0:
+                store.sharded_append_commit(name, len(records), is_writer=True)
+            self._barrier()
+            if self.rank != 0:
+                store.sharded_append_commit(name, len(records), is_writer=False)
+            # serve: merged top-k over all shards (engine/shard.py: local scan, peer-store exchange, merge)
+            self.shard_group = shard.ShardGroup(store.cols[name].index, row_offset=lo, rank=self.rank, world=self.world)
+            store.attach_group(name, self.shard_group)
+            logger.info(f"分片构建完成: 向量化 {stats['encode_s']:.2f}s, 插入 {stats['insert_s']:.2f}s")
+            return True
+        except Exception as e:
+            logger.error(f"向量化和索引失败: {e}")
+            return False
+
     # reference :194-260
     def vectorize_and_index(self, records: List[Dict]) -> bool:
+        if self.world > 1:
+            return self.vectorize_and_index_sharded(records)
         logger.info(f"开始向量化 {len(records)} 条记录")
+        import time
+        stats = {"records": len(records), "encode_s": 0.0, "insert_s": 0.0, "load_s": 0.0}
+        self.last_build_stats = stats
         try:
             batch_size = self._calculate_optimal_batch_size(len(records))
             total_batches = (len(records) + batch_size - 1) // batch_size
@@ -159,28 +218,40 @@ class DatabaseBuilder:
             for lo in range(0, len(records), chunk):
                 part = records[lo:lo + chunk]
                 texts = [r.get("semantic_text", r.get("preferred_zh", "")) for r in part]
+                t0 = time.perf_counter()
                 try:
                     vectors = self.embedding_service.encode_queries(texts)     # one GPU pass
                     failed = False
                 except Exception as e:
                     logger.error(f"记录 {part[0].get('code')}.. 向量化失败: {e}")
                     failed = True
-                for blo in range(0, len(part), batch_size):
-                    batch_records = part[blo:blo + batch_size]
-                    if failed:
-                        # the reference substitutes plain-list zero vectors (:231-232), which
-                        # insert_records then rejects (no .tolist()) -> the build aborts
-                        batch_embeddings = [[0.0] * self.milvus_service.dimension for _ in batch_records]
-                    else:
-                        batch_embeddings = [vectors[blo + i] for i in range(len(batch_records))]
-                    batch_idx += 1
-                    if not self.milvus_service.insert_records(batch_records, batch_embeddings):
+                t1 = time.perf_counter()
+                stats["encode_s"] += t1 - t0
+                if failed:
+                    # the reference substitutes plain-list zero vectors (:231-232), which insert_records then
+                    # rejects (no .tolist()) -> the build aborts
+                    for blo in range(0, len(part), batch_size):
+                        batch_records = part[blo:blo + batch_size]
+                        batch_idx += 1
+                        zeros = [[0.0] * self.milvus_service.dimension for _ in batch_records]
+                        if not self.milvus_service.insert_records(batch_records, zeros):
+                            logger.error(f"批次 {batch_idx} 插入失败...")
+                            return False
+                else:
+                    # the records of this chunk in their original order, as ONE array: the rows the reference inserts
+                    # batch by batch (:246-252) end up in the same order with the same auto ids
+                    batch_idx += (len(part) + batch_size - 1) // batch_size
+                    if not self.milvus_service.insert_records_array(part, vectors):
                         logger.error(f"批次 {batch_idx} 插入失败...")
                         return False
+                stats["insert_s"] += time.perf_counter() - t1
                 logger.info(f"✅ 已处理 {min(lo + chunk, len(records))}/{len(records)} 条记录")
             logger.info("向量化和索引建立完成")
+            t2 = time.perf_counter()
             if not self.milvus_service.load_collection():
                 logger.warning("集合加载失败，但数据插入成功")
+            stats["load_s"] = time.perf_counter() - t2
+            logger.info(f"构建耗时: 向量化 {stats['encode_s']:.2f}s, 插入 {stats['insert_s']:.2f}s, 加载 {stats['load_s']:.2f}s")
             return True
         except Exception as e:
             logger.error(f"向量化和索引失败: {e}")
@@ -208,10 +279,19 @@ class DatabaseBuilder:
     def build_full_database(self, input_file: str = "data/ICD_10v601.csv", rebuild: bool = False) -> bool:
         logger.info("开始完整构建ICD诊断数据库")
         try:
+            if self.world > 1 and self.rank != 0:
+                self._barrier()            # rank 0 creates the collection first; the others then map it
             self.initialize_services()
+            if self.world > 1 and self.rank == 0:
+                self._barrier()
             if rebuild:
                 logger.info("重建模式：清空现有数据")
-                self.milvus_service.clear_collection()
+                if self.rank == 0:
+                    self.milvus_service.clear_collection()
+                self._barrier()
+                if self.rank != 0:     # map the collection rank 0 has just re-created
+                    self.milvus_service._connect()
+                    self.milvus_service._setup_collection()
             else:
                 logger.info("增量模式：基于现有数据")
             records = self.load_csv_data(input_file)
@@ -238,7 +318,20 @@ def main(argv=None):
     parser.add_argument("--rebuild", action="store_true", help="重建数据库（清空现有数据）")
     parser.add_argument("--verify-only", action="store_true", help="仅验证现有数据库")
     args = parser.parse_args(argv)
-    builder = DatabaseBuilder()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        # launched with torch.distributed.run, one process per GPU: data-parallel encode, row-sharded table
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            if torch.cuda.is_available():
+                torch.cuda.set_device(local)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            else:
+                dist.init_process_group("gloo")
+    builder = DatabaseBuilder(rank=int(os.environ.get("RANK", "0")), world=world, dist=dist)
     try:
         if args.verify_only:
             builder.initialize_services()

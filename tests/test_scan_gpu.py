@@ -331,3 +331,61 @@ def test_config1_10k_queries_against_the_icd_sized_corpus(pkg, native):
     assert np.array_equal(ids[nq // 2:][np.arange(nq // 2), np.argmax(raw[nq // 2:], axis=1)], planted)
     print(f"configs[1]: {nq} queries x {n} rows in {wall * 1e3:.1f} ms through the C ABI with host buffers "
           f"({nq / wall:.0f} queries/s; corpus 62 MB, L2-resident)")
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs[3]
+@pytest.fixture(scope="module")
+def corpus_10m():
+    """10 M x 768 bf16 rows on the GPU (configs[3]), built like bench.py's corpus, + 1024 queries of which every 4th is a
+    perturbed corpus row."""
+    import torch
+    import bench
+    dev = torch.device("cuda", 0)
+    table, levels = bench.make_corpus(torch, 10_000_000, dev, seed=4321)
+    q, pos, gid = bench.make_planted_queries(torch, None, table, 0, 10_000_000, 10_000_000, 1024, dev, 0, 1)
+    yield table, levels, q, pos, gid
+    del table, levels
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B", [128, 256, 1024])
+def test_config3_10m_rows_against_an_independent_exact_search(pkg, native, corpus_10m, B):
+    """configs[3] with the DEFAULT launch configuration (sampling pre-pass, cross-CTA pruning, drift limiter, CTA pairs,
+    unrolled issue loop) against an independent exact search on the same GPU: chunked fp32 torch.matmul + topk, merged
+    by (score desc, id asc).  Ids identical except swaps among scores tied within 1e-6; planted rows first."""
+    import torch
+    from importlib import import_module
+    table, levels, q_all, pos, gid = corpus_10m
+    q = q_all[:B].contiguous()
+    VectorIndex = import_module("rag-project-icd10_b200.engine.index").VectorIndex
+    idx = VectorIndex(768, device=0)
+    idx.adopt(table, levels)
+    score, raw, ids = idx.search(q, 10, weight_mode=native.WEIGHT_NONE)
+    torch.cuda.synchronize()
+    qf = q.float()
+    best_s = torch.full((B, 0), -float("inf"), device=q.device)
+    best_i = torch.zeros((B, 0), dtype=torch.int64, device=q.device)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for lo in range(0, table.shape[0], 1 << 20):
+            s = qf @ table[lo:lo + (1 << 20)].float().T
+            ts, ti = s.topk(16, dim=1)
+            best_s = torch.cat([best_s, ts], 1)
+            best_i = torch.cat([best_i, ti + lo], 1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    order = best_i.argsort(dim=1, stable=True)
+    best_s, best_i = best_s.gather(1, order), best_i.gather(1, order)
+    order = (-best_s).argsort(dim=1, stable=True)[:, :10]
+    ref_s, ref_i = best_s.gather(1, order).cpu().numpy(), best_i.gather(1, order).cpu().numpy()
+    swaps = check_topk(ids.cpu().numpy(), raw.cpu().numpy(), ref_i, ref_s,
+                       lambda b, i: (table[torch.as_tensor(np.asarray(i), device=q.device)].float() @ qf[b]).cpu().numpy(),
+                       tie_tol=1e-6, score_tol=2e-6)
+    assert swaps <= B // 16, swaps
+    planted = [j for j in range(len(pos)) if pos[j] < B]
+    assert ids[[pos[j] for j in planted], 0].cpu().tolist() == [gid[j] for j in planted]
+    # the level re-rank on top of the same raw list
+    s2, r2, i2 = idx.search(q, 10, weight_mode=native.WEIGHT_RERANK)
+    assert torch.equal(i2.sort(dim=1).values, ids.sort(dim=1).values) and bool((s2[:, 1:] <= s2[:, :-1]).all())
+    idx.close()

@@ -165,3 +165,132 @@ def test_build_database_end_to_end(tmp_path, monkeypatch, model_dir):
     b2.initialize_services()
     assert b2.milvus_service.get_collection_stats()["num_entities"] == 2600
     b2.milvus_service.disconnect()
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs[0]
+@pytest.fixture(scope="module")
+def model_dir12(tmp_path_factory):
+    recs = otext.load_records(os.path.join(ROOT, "data", "ICD_10v601.csv"))
+    texts = [otext.query_text(r["semantic_text"]) for r in recs] + [otext.query_text("急性胃肠炎 发热")]
+    vocab = oenc.make_vocab(texts)
+    state = oenc.synthetic_state_dict(seed=2, num_layers=12, vocab_size=len(vocab))
+    d = str(tmp_path_factory.mktemp("model12"))
+    oenc.save_hf_dir(d, state, vocab, 12)
+    return d, state, recs
+
+
+def _pct(xs, p):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(p * len(xs)))]
+
+
+def test_config0_full_csv_build_query_and_batch1_latency(tmp_path, monkeypatch, model_dir12):
+    """BASELINE configs[0] at full size: tools/build_database.py --rebuild over all 40 474 rows of data/ICD_10v601.csv
+    (12-layer encoder, synthetic weights), the README's example query, parity of the stored vectors and of the search
+    against the oracle, and the reference's live pattern -- batch-1 encode_query + search -- timed per call.  The
+    timings go to gpurun_out/r02_config0.json (copied to profiles/ by the builder)."""
+    import time
+    d, state, recs = model_dir12
+    monkeypatch.setenv("EMBEDDING_MODEL_NAME", d)
+    monkeypatch.setenv("EMBEDDING_DEVICE", "auto")
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "db" / "icd.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "icd10")
+    monkeypatch.chdir(tmp_path)
+    B = importlib.import_module("rag-project-icd10_b200.tools.build_database")
+    csv_path = os.path.join(ROOT, "data", "ICD_10v601.csv")
+    builder = B.DatabaseBuilder()
+    t0 = time.perf_counter()
+    builder.initialize_services()
+    t_init = time.perf_counter() - t0
+    builder.milvus_service.clear_collection()
+    t0 = time.perf_counter()
+    records = builder.load_csv_data(csv_path)
+    t_csv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    assert builder.vectorize_and_index(records) is True
+    t_build = time.perf_counter() - t0
+    es, ms = builder.embedding_service, builder.milvus_service
+    enc_stats = dict(es.model.last_stats)
+    assert len(records) == 40474 and ms.get_collection_stats()["num_entities"] == 40474
+    ver = builder.verify_database()
+    assert "error" not in ver and ver["search_test"]["results_count"] == 5
+
+    # the README's example query (BASELINE configs[0]): /query '急性胃肠炎 发热', top_k = 5
+    hits = ms.search(es.encode_query("急性胃肠炎 发热"), top_k=5)
+    assert len(hits) == 5 and [h["score"] for h in hits] == sorted((h["score"] for h in hits), reverse=True)
+    assert all(set(h) == {"code", "title", "score", "original_score", "metadata"} for h in hits)
+
+    # parity 1: stored vectors vs the oracle encoder on a 200-row sample (the full corpus is ~5 CPU-minutes)
+    from parity import COS_MIN, check_topk, cosine_rows
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(len(records), size=200, replace=False))
+    oracle = oenc.OracleEncoder(state, os.path.join(d, "vocab.txt"), 12)
+    ref = oracle.encode([otext.query_text(records[j]["semantic_text"]) for j in pick], batch_size=32)
+    index = ms.client.cols["icd10"].index
+    stored = index.read(0, len(records))
+    assert cosine_rows(stored[pick], ref).min() >= COS_MIN
+    # parity 2: 200 queries through the service vs an exact fp32 search (numpy) over the same stored table
+    probes = [records[j]["preferred_zh"] for j in pick]
+    qv = es.encode_queries(probes)
+    ref_s, ref_i = osearch.exact_topk(stored, qv, 10)
+    got = ms.search_batch(qv, top_k=10)
+    got_ids = np.array([c.row_ids for c in got])
+    got_raw = np.array([c.raw_scores for c in got])
+    check_topk(got_ids, got_raw, ref_i, ref_s, lambda b, i: stored[np.asarray(i)] @ qv[b], score_tol=2e-6)
+    for b in (0, 57, 199):          # the lazy batch rows are what search() returns
+        one = ms.search(qv[b], top_k=10)
+        assert list(got[b]) == one and got[b] == one
+        assert [h["code"] for h in one] == [records[int(j)]["code"] for j in got[b].row_ids]
+
+    # the reference's live pattern (multi_diagnosis_service.py:152-153): batch-1 encode_query, then search
+    for _ in range(20):
+        ms.search(es.encode_query(probes[0]), top_k=10)
+    t_enc, t_search = [], []
+    for i in range(1000):
+        text = probes[i % len(probes)]
+        t0 = time.perf_counter()
+        v = es.encode_query(text)
+        t1 = time.perf_counter()
+        ms.search(v, top_k=10)
+        t2 = time.perf_counter()
+        t_enc.append((t1 - t0) * 1e3)
+        t_search.append((t2 - t1) * 1e3)
+    # batched replacement of the per-diagnosis loop: 1 encode + 1 scan for a whole request
+    R = importlib.import_module("rag-project-icd10_b200.services.batched_retrieval")
+    br = R.BatchedRetrieval(es, ms)
+    req = probes[:8]
+    t0 = time.perf_counter()
+    seq = [ms.search(es.encode_query(t), top_k=10) for t in req]
+    t_seq = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    bat = br.retrieve(req, top_k=5)        # limit = top_k * 2 = 10, as in the reference
+    bat = [list(c) for c in bat]
+    t_bat = (time.perf_counter() - t0) * 1e3
+    for a, b in zip(seq, bat):
+        assert len(a) == len(b) == 10
+        # the encoder pads a batch to its longest member: embeddings agree to ~1e-5, ids up to near-ties
+        sa = {h["code"]: h["original_score"] for h in a}
+        assert len(set(sa) & {h["code"] for h in b}) >= 9
+        for h in b:
+            if h["code"] in sa:
+                assert abs(h["original_score"] - sa[h["code"]]) < 1e-3
+    out = {"rows": len(records), "init_s": t_init, "csv_s": t_csv, "build_s": t_build, "build_split": builder.last_build_stats,
+           "encoder_stats": {k: v for k, v in enc_stats.items()},
+           "encode_query_ms": {"p50": _pct(t_enc, 0.5), "p99": _pct(t_enc, 0.99), "mean": sum(t_enc) / len(t_enc)},
+           "search_ms": {"p50": _pct(t_search, 0.5), "p99": _pct(t_search, 0.99), "mean": sum(t_search) / len(t_search)},
+           "request_of_8_diagnoses_ms": {"sequential": t_seq, "batched": t_bat},
+           "example_query": [{"code": h["code"], "title": h["title"], "score": h["score"]} for h in hits],
+           "layers": 12, "weights": "synthetic (no checkpoint offline)", "host_threads": os.cpu_count()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "r02_config0.json"), "w", encoding="utf-8") as fh:
+        json.dump(out, fh, ensure_ascii=False, indent=1)
+    print(json.dumps(out, ensure_ascii=False)[:1500])
+    assert t_build < 15.0, t_build
+    assert out["encode_query_ms"]["p50"] < 10.0 and out["search_ms"]["p50"] < 10.0
+    ms.disconnect()
+    # a fresh process state maps the columnar store back and answers the same query identically
+    b2 = B.DatabaseBuilder()
+    b2.initialize_services()
+    again = b2.milvus_service.search(b2.embedding_service.encode_query("急性胃肠炎 发热"), top_k=5)
+    assert [h["code"] for h in again] == [h["code"] for h in hits]
+    b2.milvus_service.disconnect()
