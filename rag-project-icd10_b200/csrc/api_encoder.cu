@@ -363,7 +363,10 @@ static int encode_hidden(icd_encoder* e, const int32_t* ids, const int32_t* lens
   // ids outside the embedding table read [UNK] (100 in BERT vocabularies) instead of faulting
   const int unk = e->cfg.vocab_size > 100 ? 100 : 0;
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->cfg.vocab_size, unk, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
-  auto attention = [&]() { return launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st); };
+  auto attention = [&]() {
+    return S <= 128 ? launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st)
+                    : launch_attention_long(e->qkv, d_lens, B, S, e->ctx, st);
+  };
   const void* final_h = e->h;
   if (e->fused_ln) {
     // Deferred LayerNorm: e->h carries the layer input -- normalised for layer 0 (embed_ln), the un-normalised
@@ -431,7 +434,7 @@ extern "C" {
 int icd_encoder_forward(icd_encoder* e, const int32_t* ids, const int32_t* lens, int B, int S, void* out,
                         int out_dtype, void* stream, int sync) {
   ICD_CHECK_ARG(e != nullptr, "encoder is null");
-  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 128, "need 1 <= S <= 128");
+  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 512, "need 1 <= S <= 512");
   ICD_CHECK_ARG(S <= e->cfg.max_position, "S exceeds max_position");
   const int out_flags = out_dtype;
   out_dtype &= 0xff;
@@ -490,7 +493,7 @@ int icd_encoder_token_logits(icd_encoder* e, const int32_t* ids, const int32_t* 
                              void* stream, int sync) {
   ICD_CHECK_ARG(e != nullptr, "encoder is null");
   ICD_CHECK_ARG(e->head_labels > 0, "no token head: call icd_encoder_set_token_head first");
-  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 128, "need 1 <= S <= 128");
+  ICD_CHECK_ARG(B >= 0 && S >= 1 && S <= 512, "need 1 <= S <= 512");
   ICD_CHECK_ARG(S <= e->cfg.max_position, "S exceeds max_position");
   if (B == 0) return ICD_OK;
   ICD_CHECK_ARG(ids && lens && out, "null buffer");

@@ -18,7 +18,7 @@ from .. import _native as N
 from . import weights as W
 from .tokenizer import NativeTokenizer
 
-MAX_S = 128  # kernel limit == sentence-transformers max_seq_length of text2vec-base-chinese
+MAX_S = 512  # kernel limit (BERT's position table); text2vec-base-chinese's own max_seq_length is 128
 FEED_CHUNK = 32768   # sentences tokenised / length-bucketed / copied back as one unit of the feeder pipeline
 SMALL_BATCH = 256    # up to this many sentences take the direct path (one tokeniser call, synchronous launches)
 

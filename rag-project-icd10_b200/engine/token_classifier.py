@@ -9,13 +9,14 @@ the "simple" grouping of adjacent tokens stay on the host, as they do inside the
 (third party, transformers TokenClassificationPipeline: postprocess / gather_pre_entities / aggregate /
 group_entities; restated here, checked against the pipeline itself in tests/test_ner_*.py).
 
-Long texts.  The kernels take sequences of at most 128 tokens; the reference pipeline reads up to the model's 512.
-A text that does not fit one window is cut into overlapping windows (the tokenizer's own overflow mechanism,
-`stride` tokens of overlap) that go through the GPU as one batch, and the windows' entities are merged with the
-pipeline's rule for exactly this case (aggregate_overlapping_entities: of two overlapping entities the longer
-wins, then the higher score) -- the algorithm of ``pipeline(..., stride=n)``.  Tokens beyond the reference's own
-512-token horizon are dropped, as they are there.  Texts of up to 126 tokens (every diagnosis string in the
-reference's data) take the single-window path and are unaffected.
+Long texts.  The encoder takes sequences of up to 512 tokens (S <= 128 on the tensor-core attention kernel, longer ones
+on the shared-memory kernel of csrc/encoder_kernels.cu), so a model with a 512-token position table reads a text in ONE
+pass truncated at 512 tokens, exactly like the reference pipeline.  When the window is shorter than the horizon (an
+encoder built with a smaller max_seq_length), a text that does not fit is cut into overlapping windows (the
+tokenizer's own overflow mechanism, `stride` tokens of overlap) that go through the GPU as one batch, and the windows'
+entities are merged with the pipeline's rule for exactly this case (aggregate_overlapping_entities: of two
+overlapping entities the longer wins, then the higher score) -- the algorithm of ``pipeline(..., stride=n)``.  Tokens
+beyond the reference's 512-token horizon are dropped, as they are there.
 """
 from __future__ import annotations
 
@@ -132,7 +133,7 @@ class TokenClassifierEngine:
         self.id2label = id2label or {i: f"LABEL_{i}" for i in range(n)}
         if len(self.id2label) != n:
             raise ValueError("id2label does not match the classifier head")
-        self.max_seq_length = self.encoder.max_seq_length   # kernel limit 128 tokens per sequence
+        self.max_seq_length = self.encoder.max_seq_length   # tokens per window (<= 512, the kernel limit)
         self.stride = int(stride)                            # overlap of the windows of a long text, in tokens
         self.horizon = int(horizon)                          # the reference pipeline truncates at model_max_length
 
@@ -157,7 +158,9 @@ class TokenClassifierEngine:
         for w, t in enumerate(owner):
             k = seen.get(t, 0)
             seen[t] = k + 1
-            if k * step < max(1, self.horizon - 2):
+            # a model that reads the whole horizon in one pass (max_seq_length >= 512) sees exactly the reference's
+            # single truncated window; shorter windows tile the horizon with `stride` tokens of overlap
+            if (k == 0) if self.max_seq_length >= self.horizon else (k * step < max(1, self.horizon - 2)):
                 keep.append(w)
         per_window: Dict[int, List[dict]] = {}
         order = sorted(keep, key=lambda w: -len(ids[w]))

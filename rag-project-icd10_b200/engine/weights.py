@@ -115,8 +115,6 @@ def load_model_dir(path: str) -> Tuple[N.BertCfg, np.ndarray, dict]:
     if meta["do_lower_case_text"]:
         raise ValueError(f"{path}: sentence_bert_config.json asks for text lower-casing before tokenisation, which this "
                          "engine does not apply")
-    if meta["max_seq_length"] > 128:
-        import warnings
-        warnings.warn(f"{path}: max_seq_length {meta['max_seq_length']} exceeds this engine's 128-token kernel limit; "
-                      "inputs are truncated at 128 tokens (text2vec-base-chinese uses 128)", RuntimeWarning, stacklevel=2)
+    if meta["max_seq_length"] > 512:
+        raise ValueError(f"{path}: max_seq_length {meta['max_seq_length']} exceeds this engine's 512-token limit")
     return cfg, pack_state_dict(state, cfg), meta

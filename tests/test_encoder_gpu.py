@@ -50,7 +50,7 @@ def small():
     eng.close()
 
 
-@pytest.mark.parametrize("B,S", [(1, 1), (1, 7), (5, 24), (3, 64), (2, 128), (37, 33), (130, 16)])
+@pytest.mark.parametrize("B,S", [(1, 1), (1, 7), (5, 24), (3, 64), (2, 128), (37, 33), (130, 16), (2, 129), (3, 300), (2, 512)])
 def test_forward_matches_oracle(small, B, S):
     eng, state, layers, vocab = small
     rng = np.random.default_rng(B * 1000 + S)

@@ -82,3 +82,25 @@ def test_token_head_errors(ner):
     with pytest.raises(N.NativeError):
         eng.encoder.set_token_head(np.zeros((N.MAX_LABELS + 1, 768), np.float32), np.zeros(N.MAX_LABELS + 1, np.float32))
     eng.encoder.set_token_head(*[np.asarray(p.detach().numpy(), np.float32) for p in (model.classifier.weight, model.classifier.bias)])
+
+
+def test_long_text_is_read_in_one_pass_like_the_reference_pipeline(ner):
+    """A ~400-token text: the reference pipeline reads it in one 512-token pass (medical_ner_service.py:177-229).  So
+    does the engine (sequences beyond 128 tokens take the long-sequence attention kernel): logits against the fp32 HF
+    model, entity groups against the pipeline without stride."""
+    nc, eng, model, tok = ner
+    assert eng.max_seq_length == 512
+    long_text = ",".join(nc.TEXTS * 5)
+    ids = np.asarray(tok(long_text, truncation=True, max_length=512)["input_ids"], np.int32)[None, :]
+    assert 128 < ids.shape[1] <= 512
+    ref = nc.hf_logits(model, tok, long_text, max_length=512)
+    got = eng.encoder.token_logits(ids, np.array([ids.shape[1]], np.int32))[0]
+    assert got.shape == ref.shape
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() >= 0.999 and float(np.abs(got - ref).max() / np.abs(ref).max()) <= 0.03
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    if (top2[:, 1] - top2[:, 0]).min() >= 0.25:
+        nc.same_groups(eng(long_text), nc.hf_pipeline(model, tok)(long_text), score_tol=0.03)
+    # a batch mixing short and long texts: every text equals its own single call
+    both = eng([nc.TEXTS[0], long_text, nc.TEXTS[1]])
+    assert [len(x) for x in both] == [len(eng(nc.TEXTS[0])), len(eng(long_text)), len(eng(nc.TEXTS[1]))]
