@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 N = importlib.import_module("rag-project-icd10_b200._native")
+if os.environ.get("PROF_LIB"):      # a profiling build of the library (make PROFILING=1), e.g. for layout experiments
+    N.LIB_PATH = os.path.abspath(os.environ["PROF_LIB"])
 VectorIndex = importlib.import_module("rag-project-icd10_b200.engine.index").VectorIndex
 rows, B, k = int(os.environ.get("ROWS", 100_000_000)), int(os.environ.get("BATCH", 1024)), 10
 steps = int(os.environ.get("STEPS", 5))
@@ -13,6 +15,8 @@ warm = int(os.environ.get("WARM", 2))
 variants = [v for v in os.environ.get("VARIANTS", "scan_pair=-1;scan_pair=0").split(";") if v]
 DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_kbs_pair=6, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0,
                 scan_generic=0)
+if os.environ.get("PROF_LIB"):
+    DEFAULTS["scan_tiled"] = 0
 dev = torch.device("cuda", 0)
 table, levels = bench.make_corpus(torch, rows, dev, 1234)
 q = bench.make_queries(torch, B, dev)

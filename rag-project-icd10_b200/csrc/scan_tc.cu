@@ -87,6 +87,10 @@ struct ScanParams {
   int tstride;   // scan every tstride-th row tile only (1 = all rows; > 1 = the sampling pre-pass)
   int* progress; // [G * T] tiles issued by each CTA's producer (drift limiter), or null
   int drift;     // a producer may run at most this many tiles ahead of the slowest CTA of its row group
+#ifdef ICD_PROFILING
+  int tiled;     // timing experiment: read the table AS IF it were stored tile-major [tile][K block][128 rows][64]
+                 // (8 KiB contiguous runs per K block instead of 768-byte row segments); results are meaningless
+#endif
 };
 
 // Private candidate list of one query (thread): kc entries sorted by (score desc, id asc) in
@@ -251,11 +255,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           if (NC == 1) {
             const uint32_t fb = ptx::smem_u32(&full_bar[stage]);
             ptx::mbar_expect_tx(fb, (uint32_t)stage_bytes);
+#ifdef ICD_PROFILING
+            if (p.tiled) ptx::tma_load_4d(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row % BN, kb, row / BN);
+            else
+#endif
             ptx::tma_load_3d(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
           } else {
             // both CTAs' bytes are counted on the LEADER's barrier (only its MMA thread waits for the stage)
             if (rank == 0) ptx::mbar_expect_tx(ptx::smem_u32(&full_bar[stage]), 2u * (uint32_t)stage_bytes);
             const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+#ifdef ICD_PROFILING
+            if (p.tiled) ptx::tma_load_4d_pair(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row % BN, kb, row / BN);
+            else
+#endif
             ptx::tma_load_3d_pair(ptx::smem_u32(stage_base + (size_t)stage * stage_bytes), &tmap, fb, 0, row, kb);
           }
 
@@ -526,6 +538,31 @@ int make_tmap_bf16_3d(void* map128, const void* base, uint64_t d0, uint64_t d1, 
   return ICD_OK;
 }
 
+#ifdef ICD_PROFILING
+// timing experiment only: the same bytes viewed as [tiles][K blocks][128 rows][64 elements] (tile-major)
+static int make_tmap_bf16_4d_tiled(void* map128, const void* base, uint64_t tiles, uint32_t nkb, uint32_t box_rows, uint32_t box_kb) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  ICD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres));
+  cuuint64_t gdim[4] = {64, 128, nkb, tiles};
+  cuuint64_t gstride[3] = {128, 128 * 128, (cuuint64_t)128 * 128 * nkb};
+  cuuint32_t box[4] = {64, box_rows, box_kb, 1};
+  cuuint32_t estride[4] = {1, 1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeFn>(sym)(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                               const_cast<void*>(base), gdim, gstride, box, estride,
+                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+    return ICD_E_CUDA;
+  }
+  return ICD_OK;
+}
+#endif
+
 // tuning knobs: defaults (profiling builds, -DICD_PROFILING: from the environment -- ICD_SCAN_BN = 64 | 128, ICD_SCAN_DRIFT = tiles, 0 = limiter
 // off, ICD_SCAN_TMAX = query tiles sharing one row stream per launch, ICD_SCAN_KBS = K blocks per stage,
 // ICD_SCAN_SAMPLE = pre-pass stride, 0 = off, -1 = by table size); icd_tune() overrides them at run time.
@@ -539,7 +576,7 @@ static int env_int(const char* name, int dflt) {
 #endif
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, gen;
+  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
@@ -550,6 +587,7 @@ struct Tunables {
     qsplit = env_int("ICD_SCAN_QSPLIT", -1);  // -1 auto (tensor-bound launches), 0 off, 1 always
     pair = env_int("ICD_SCAN_PAIR", -1);      // CTA pairs: -1 auto (even number of query tiles >= 2), 0 off
     qtmem = env_int("ICD_SCAN_QTMEM", 0);      // K blocks of the query tile kept in TMEM when split (0 = all that fit: 8)
+    tiled = 0;
     generic = env_int("ICD_SCAN_GENERIC", 0);   // 1 = always the generic (run-time shape) issue loop: A/B only
     gen = 0;
   }
@@ -574,6 +612,9 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_pair")) t.pair = value;
   else if (!strcmp(key, "scan_qtmem")) t.qtmem = std::max(0, value);
   else if (!strcmp(key, "scan_generic")) t.generic = value != 0;
+#ifdef ICD_PROFILING
+  else if (!strcmp(key, "scan_tiled")) t.tiled = value != 0;
+#endif
   else return ICD_E_ARG;
   ++t.gen;  // tensor maps depend on bn / kbs: indexes rebuild theirs when the generation moves
   return ICD_OK;
@@ -727,6 +768,11 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   CUtensorMap tmap;
   {
     alignas(128) unsigned char pm[128];
+#ifdef ICD_PROFILING
+    if (tun().tiled && BN == 128) {
+      ICD_TRY(make_tmap_bf16_4d_tiled(pm, a.table, (uint64_t)(a.n_rows / BN), (uint32_t)(a.dim / BK), (uint32_t)(BN / NC), (uint32_t)kbs));
+    } else
+#endif
     ICD_TRY(make_tmap_bf16_3d(pm, a.table, BK, (uint64_t)a.n_rows, (uint64_t)(a.dim / BK), (uint64_t)a.dim * 2, BK * 2, BK,
                               (uint32_t)(BN / NC), (uint32_t)kbs));
     memcpy(&tmap, pm, sizeof(CUtensorMap));
@@ -756,6 +802,9 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.tstride = tstride;
     p.drift = scan_drift();
     p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64) ? a.progress + (size_t)launch * kSMs : nullptr;
+#ifdef ICD_PROFILING
+    p.tiled = (tun().tiled && BN == 128) ? 1 : 0;
+#endif
     // specialised issue loops for the shapes the launcher actually picks at dim = 768 (everything else: generic)
     const bool spec = BN == 128 && a.dim == 768 && nkb_tmem == 8 && tun().generic == 0;
     if (pair && spec && kbs == 6) ICD_TRY((launch_one<BN, 2, 6, 8>(tmap, p, G * p.T, smem, st)));

@@ -236,6 +236,9 @@ def test_config0_full_csv_build_query_and_batch1_latency(tmp_path, monkeypatch, 
     got = ms.search_batch(qv, top_k=10)
     got_ids = np.array([c.row_ids for c in got])
     got_raw = np.array([c.raw_scores for c in got])
+    # search_batch returns the reference's order (re-sorted by level-weighted score); the exact search is by raw score
+    by_raw = np.stack([np.lexsort((got_ids[b], -got_raw[b].astype(np.float64))) for b in range(len(got))])
+    got_ids, got_raw = np.take_along_axis(got_ids, by_raw, 1), np.take_along_axis(got_raw, by_raw, 1)
     check_topk(got_ids, got_raw, ref_i, ref_s, lambda b, i: stored[np.asarray(i)] @ qv[b], score_tol=2e-6)
     for b in (0, 57, 199):          # the lazy batch rows are what search() returns
         one = ms.search(qv[b], top_k=10)
