@@ -907,4 +907,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:      # a rank that dies must take the job down (torchrun then stops the others): never hang
+        if isinstance(exc, SystemExit) and not exc.code:
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

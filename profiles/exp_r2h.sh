@@ -3,6 +3,9 @@
 # launch list of the default bench command
 OUT=gpurun_out; mkdir -p $OUT
 NCU="ncu --clock-control none"
+# can the reference's own engines run on this box?
+( python -c "import sentence_transformers" 2>&1 | tail -n 1; python -c "import pymilvus" 2>&1 | tail -n 1; python -c "import milvus_lite" 2>&1 | tail -n 1; ls -la ~/.cache/huggingface 2>&1 | head -n 5; pip download sentence-transformers --no-deps -d /tmp/x 2>&1 | tail -n 1 ) > $OUT/r02h_probe.txt 2>&1
+cat $OUT/r02h_probe.txt
 for cfg in "100000000 1024,256,128" "50000000 1024" "25000000 1024" "12500000 1024,256,128"; do
   set -- $cfg
   ROWS=$1 BATCHES=$2 timeout 900 $NCU --profile-from-start off --set full --import-source on -k regex:scan_tc -f -o $OUT/r02h_scan_$1 \

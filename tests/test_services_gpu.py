@@ -297,3 +297,54 @@ def test_config0_full_csv_build_query_and_batch1_latency(tmp_path, monkeypatch, 
     again = b2.milvus_service.search(b2.embedding_service.encode_query("急性胃肠炎 发热"), top_k=5)
     assert [h["code"] for h in again] == [h["code"] for h in hits]
     b2.milvus_service.disconnect()
+
+
+class _Emb768:
+    def encode_query(self, q):
+        return np.ones(768, np.float32) / np.sqrt(768.0)
+
+
+def test_config1_10k_queries_through_the_service_api(tmp_path, monkeypatch):
+    """BASELINE configs[1] through the reference-facing API: 10 000 query vectors against the ICD-sized table
+    (40 474 x 768, the real level bytes) in ONE MilvusService.search_batch call -- GPU scan + GPU level re-rank, hit
+    dicts built lazily -- checked against the oracle's search + re-rank on a sample and against search() row by row."""
+    import time
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "db" / "c1.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "icd10")
+    M = importlib.import_module("rag-project-icd10_b200.services.milvus_service")
+    ms = M.MilvusService(embedding_service=_Emb768())
+    recs = otext.load_records(os.path.join(ROOT, "data", "ICD_10v601.csv"))
+    rng = np.random.default_rng(5)
+    corpus = rng.standard_normal((len(recs), 768)).astype(np.float32)
+    corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    assert ms.insert_records_array(recs, corpus) is True
+    nq = 10_000
+    q = corpus[rng.integers(0, len(recs), size=nq)] + 0.05 * rng.standard_normal((nq, 768)).astype(np.float32)
+    q[nq // 2:] = rng.standard_normal((nq - nq // 2, 768)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    ms.search_batch(q[:64], top_k=10)
+    t0 = time.perf_counter()
+    got = ms.search_batch(q, top_k=10)
+    dt = time.perf_counter() - t0
+    assert len(got) == nq and all(len(c) == 10 for c in got[:50])
+    levels = np.array([r["level"] for r in recs])
+    sample = list(range(0, nq, 97))
+    ref_s, ref_i = osearch.exact_topk(corpus, q[sample], 10)
+    for n, b in enumerate(sample):
+        order, weighted = osearch.rerank(ref_s[n], levels[ref_i[n]])
+        want_codes = [recs[int(ref_i[n][j])]["code"] for j in order]
+        hits = list(got[b])
+        assert [h["code"] for h in hits] == want_codes, b
+        assert np.allclose([h["score"] for h in hits], [weighted[j] for j in order], atol=1e-6)
+        assert hits == ms.search(q[b], top_k=10)
+    t0 = time.perf_counter()
+    n_dicts = sum(len(list(c)) for c in got)
+    dt_dicts = time.perf_counter() - t0
+    print(f"configs[1] through MilvusService.search_batch: {nq} queries in {dt * 1e3:.1f} ms ({nq / dt:.0f} queries/s); "
+          f"materialising all {n_dicts} hit dicts: {dt_dicts * 1e3:.0f} ms")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "r02_config1.json"), "w") as fh:
+        json.dump({"queries": nq, "rows": len(recs), "search_batch_ms": dt * 1e3, "queries_per_s": nq / dt,
+                   "materialise_all_hit_dicts_ms": dt_dicts * 1e3, "hit_dicts": n_dicts}, fh)
+    assert dt < 2.0
+    ms.disconnect()
