@@ -328,13 +328,22 @@ class HierarchicalSimilarityService:
     def batch_calculate_similarities_many(self, requests):
         """All diagnoses of a request in one call: `requests` is a list of (query_text, query_entities,
         candidate_records) -- e.g. one entry per extracted diagnosis with the rows MilvusService.search_batch
-        returned for it.  The string-dependent factors are computed per (query, candidate) on the host exactly as
-        in batch_calculate_similarities; the weighted score of ALL pairs is then one vectorised pass
-        (weighted_scores).  Returns one list per request, identical -- records, scores, factors, order -- to
-        calling batch_calculate_similarities(query_text, query_entities, candidate_records) on each."""
+        returned for it.
+
+        The reference's per-candidate loop encodes TWO texts per candidate for the semantic-coherence factor
+        (_calculate_semantic_coherence, reference :388-412: the query and the candidate's semantic_text, batch 1
+        each) -- 40 encoder forwards for the 20 candidates of one diagnosis, the dominant cost of a request.  Here
+        every distinct text of the whole request goes through the encoder ONCE, in one batch
+        (EmbeddingService.encode_queries), and the factor is a dot product of cached vectors; the other
+        string-dependent factors are computed per (query, candidate) on the host exactly as in
+        batch_calculate_similarities, and the weighted score of ALL pairs is one vectorised pass (weighted_scores).
+        Returns one list per request with the records, factors and order of batch_calculate_similarities(query_text,
+        query_entities, candidate_records) on each -- bit-identical when the embedding service is deterministic per
+        text (the golden test), within the encoder's batch-composition noise (~1e-6) on the GPU."""
         plans, rows = [], []          # rows: (request index, record, factors | None, exact)
-        for ri, (query_text, query_entities, candidate_records) in enumerate(requests):
-            core, candidates = self.uncertainty_service.process_uncertainty_query(query_text, candidate_records)
+        prepared = [(self.uncertainty_service.process_uncertainty_query(q, c), e) for q, e, c in requests]
+        vec_of = self._encode_request_texts(prepared)
+        for ri, ((core, candidates), query_entities) in enumerate(prepared):
             plans.append(len(candidates))
             for rec in candidates:
                 factors = SimilarityFactors()
@@ -345,7 +354,7 @@ class HierarchicalSimilarityService:
                         factors.vector_similarity = 1.0
                     factors.hierarchy_boost = self._calculate_hierarchy_boost(core, query_entities, rec)
                     factors.entity_match_score = self._calculate_entity_match_score(query_entities, rec)
-                    factors.semantic_coherence = self._calculate_semantic_coherence(core, rec)
+                    factors.semantic_coherence = self._semantic_coherence_cached(core, rec, vec_of)
                     factors.category_alignment = self._calculate_category_alignment(query_entities, rec)
                     factors.context_relevance = self._calculate_context_relevance(core, rec)
                     rows.append((ri, rec, factors, exact, True))
@@ -372,6 +381,44 @@ class HierarchicalSimilarityService:
         for lst in out:
             lst.sort(key=lambda t: t[1], reverse=True)
         return out
+
+    def _encode_request_texts(self, prepared) -> Dict[str, Any]:
+        """text -> embedding for every distinct text the semantic-coherence factor of a request needs (the core query of
+        every diagnosis, the semantic_text of every candidate): one encode_queries call, or {} when that fails / there
+        is no embedding service (the factor then falls back to the per-candidate path and its defaults)."""
+        if not self.embedding_service:
+            return {}
+        texts, seen = [], set()
+        for (core, candidates), _entities in prepared:
+            for t in [core] + [rec.get("semantic_text", "") for rec in candidates]:
+                if t and t not in seen:
+                    seen.add(t)
+                    texts.append(t)
+        if not texts:
+            return {}
+        try:
+            many = getattr(self.embedding_service, "encode_queries", None)
+            vecs = many(texts) if many is not None else [self.embedding_service.encode_query(t) for t in texts]
+            return {t: v for t, v in zip(texts, vecs)}
+        except Exception as e:
+            logger.warning(f"批量语义向量计算失败: {e}")
+            return {}
+
+    def _semantic_coherence_cached(self, query_text, candidate_record, vec_of) -> float:
+        """_calculate_semantic_coherence (reference :388-412) over the vectors of _encode_request_texts."""
+        if not self.embedding_service:
+            return 0.5
+        text = candidate_record.get("semantic_text", "")
+        if not text:
+            return 0.3
+        qv, sv = vec_of.get(query_text), vec_of.get(text)
+        if qv is None or sv is None:
+            return self._calculate_semantic_coherence(query_text, candidate_record)
+        try:
+            return max(_cosine(qv, sv), 0.0)
+        except Exception as e:
+            logger.warning(f"语义一致性计算失败: {e}")
+            return 0.5
 
     # reference :581-624
     def get_similarity_explanation(self, factors: SimilarityFactors) -> Dict[str, Any]:

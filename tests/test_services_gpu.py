@@ -277,7 +277,25 @@ def test_config0_full_csv_build_query_and_batch1_latency(tmp_path, monkeypatch, 
         for h in b:
             if h["code"] in sa:
                 assert abs(h["original_score"] - sa[h["code"]]) < 1e-3
+    # ... and the re-scoring on top (multi_diagnosis_service.py:156-158): the reference encodes two texts PER CANDIDATE
+    # for the semantic-coherence factor; the batched path encodes every distinct text of the request once
+    H = importlib.import_module("rag-project-icd10_b200.services.hierarchical_similarity_service")
+    hs = H.HierarchicalSimilarityService(embedding_service=es)
+    br2 = R.BatchedRetrieval(es, ms, hierarchical_similarity=hs)
+    ents = [{"disease": [{"text": t, "confidence": 0.9}], "symptom": [], "anatomy": []} for t in req]
+    t0 = time.perf_counter()
+    seq_e = [hs.batch_calculate_similarities(t, e, ms.search(es.encode_query(t), top_k=10))[:5] for t, e in zip(req, ents)]
+    t_seq_e = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    bat_e = br2.retrieve_enhanced(req, ents, top_k=5)
+    t_bat_e = (time.perf_counter() - t0) * 1e3
+    for a, b in zip(seq_e, bat_e):
+        assert len(a) == len(b) == 5
+        sa = {rec["code"]: score for rec, score, _ in a}
+        common = [(rec["code"], score) for rec, score, _ in b if rec["code"] in sa]
+        assert len(common) >= 4 and all(abs(score - sa[code]) < 1e-3 for code, score in common)
     out = {"rows": len(records), "init_s": t_init, "csv_s": t_csv, "build_s": t_build, "build_split": builder.last_build_stats,
+           "request_of_8_diagnoses_with_rescoring_ms": {"sequential": t_seq_e, "batched": t_bat_e},
            "encoder_stats": {k: v for k, v in enc_stats.items()},
            "encode_query_ms": {"p50": _pct(t_enc, 0.5), "p99": _pct(t_enc, 0.99), "mean": sum(t_enc) / len(t_enc)},
            "search_ms": {"p50": _pct(t_search, 0.5), "p99": _pct(t_search, 0.99), "mean": sum(t_search) / len(t_search)},
