@@ -332,6 +332,7 @@ def main(argv=None):
             else:
                 dist.init_process_group("gloo")
     builder = DatabaseBuilder(rank=int(os.environ.get("RANK", "0")), world=world, dist=dist)
+    own_group = world > 1
     try:
         if args.verify_only:
             builder.initialize_services()
@@ -353,6 +354,15 @@ def main(argv=None):
         logger.error(f"运行出错: {e}")
         print(f"错误: {e}")
         return False
+    finally:
+        if own_group and dist is not None and dist.is_initialized():
+            try:
+                if builder.shard_group is not None:
+                    builder.shard_group.close()
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:
+                pass
 
 
 if __name__ == "__main__":
