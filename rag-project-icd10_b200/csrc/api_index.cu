@@ -109,7 +109,7 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
   kc = std::max(kc, k);
 
   const int P = use_tc ? tensor_scan_max_partials() : stream_scan_grid();
-  ICD_TRY(x->part_score.reserve((size_t)B * P * kc * 4));
+  ICD_TRY(x->part_score.reserve((size_t)B * P * std::max(kc, use_tc ? tensor_scan_pre_slots() : kc) * 4));
   ICD_TRY(x->part_id.reserve((size_t)B * P * kc * 4));
   ICD_TRY(x->cand_score.reserve((size_t)B * kc * 4));
   ICD_TRY(x->cand_id.reserve((size_t)B * kc * 8));
@@ -158,23 +158,32 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
       const int sample = tensor_scan_sample_stride(n);
       ICD_CUDA(cudaMemsetAsync(x->gbound.ptr, 0x80, (size_t)B * 4, st));
       if (sample > 1) {
-        // sampling pre-pass: exact top-kc of every `sample`-th row tile; its kc-th best score is a
-        // proven lower bound of the final kc-th best, so the main scan admits only rows that reach
-        // it (about kc * sample rows per query instead of every row of each list's warm-up)
+        // sampling pre-pass over every `sample`-th row tile: a proven lower bound of the final kc-th best score per
+        // query, so the main scan admits only rows that reach it (about kc * sample rows per query instead of every row
+        // of each list's warm-up).  kc <= 32: slot maxima, no lists (scan_tc.cu, PRE); larger kc: exact top-kc of the
+        // sample through the list path and the merge.
         a.tile_stride = sample;
-        ICD_TRY(launch_tensor_scan(a, x->tmap, st));
-        MergeArgs m{};
-        m.part_score = (const float*)x->part_score.ptr;
-        m.part_id = (const int*)x->part_id.ptr;
-        m.B = B;
-        m.P = P_used;
-        m.k_in = kc;
-        m.k_out = kc;
-        m.out_score = (float*)x->cand_score.ptr;
-        m.out_id = (int64_t*)x->cand_id.ptr;
-        m.row_offset = 0;
-        m.bound_key_out = (int*)x->gbound.ptr;
-        ICD_TRY(launch_merge(m, st));
+        if (kc <= tensor_scan_pre_slots() && tensor_scan_pre_mode() != 0) {
+          a.pre_slots = 1;
+          ICD_TRY(launch_tensor_scan(a, x->tmap, st));
+          a.pre_slots = 0;
+          ICD_TRY(launch_bound_from_slots((const float*)x->part_score.ptr, B, P_used, tensor_scan_pre_slots(), kc,
+                                          (int*)x->gbound.ptr, st));
+        } else {
+          ICD_TRY(launch_tensor_scan(a, x->tmap, st));
+          MergeArgs m{};
+          m.part_score = (const float*)x->part_score.ptr;
+          m.part_id = (const int*)x->part_id.ptr;
+          m.B = B;
+          m.P = P_used;
+          m.k_in = kc;
+          m.k_out = kc;
+          m.out_score = (float*)x->cand_score.ptr;
+          m.out_id = (int64_t*)x->cand_id.ptr;
+          m.row_offset = 0;
+          m.bound_key_out = (int*)x->gbound.ptr;
+          ICD_TRY(launch_merge(m, st));
+        }
         a.tile_stride = 1;
         a.progress += prog_ints;
       }

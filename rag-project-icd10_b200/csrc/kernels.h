@@ -42,7 +42,11 @@ struct TensorScanArgs {
   int* gbound;        // [B] ints, pre-set to 0x80808080 (a very negative key), or null to disable pruning
   int* progress;      // [tensor_scan_progress_ints()] zeroed ints for the drift limiter, or null
   int tile_stride;    // 0/1: scan every row; s > 1: scan every s-th 128-row tile only (sampling pre-pass)
+  int pre_slots;      // != 0 (with tile_stride > 1): slot-maxima pre-pass -- part_score receives [B, groups, tensor_scan_pre_slots()]
+                      // running maxima instead of sorted lists, part_id is untouched; feed launch_bound_from_slots
 };
+int tensor_scan_pre_slots();
+int tensor_scan_pre_mode();   // 1 = slot-maxima pre-pass (default), 0 = list-based pre-pass (icd_tune "scan_pre_slots")
 // stride of the sampling pre-pass for a table of n_rows (0 = no pre-pass)
 int tensor_scan_sample_stride(int64_t n_rows);
 // run-time tuning (icd_tune); the generation moves whenever a knob that shapes the TMA descriptor changes
@@ -68,6 +72,10 @@ struct MergeArgs {
                              // the list holds fewer than k_out rows) -- the admission bound of the main scan
 };
 int launch_merge(const MergeArgs& a, cudaStream_t st);
+// pre-pass bound: per query the kc-th largest of the slot maxima (each slot's maximum taken over the P groups) as an
+// order-preserving key in bound_key_out[b]; slots is tensor_scan_pre_slots() (32), kc <= slots
+int launch_bound_from_slots(const float* slot_max /*[B, P, slots]*/, int B, int P, int slots, int kc, int* bound_key_out,
+                            cudaStream_t st);
 
 // fused exchange, producer side: per-peer destinations of this rank's (raw, id, level) block
 struct PushTargets {

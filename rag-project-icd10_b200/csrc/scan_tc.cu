@@ -67,6 +67,7 @@ constexpr int kMaxStages = 12;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kPreSlots = 32;  // running maxima per query in the pre-pass (>= kc of every launch that uses it)
 
 struct ScanParams {
   const uint8_t* levels;
@@ -115,7 +116,14 @@ __device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, i
 // loop (KBS = 0: run-time kbs / nkb_tmem, 64-bit descriptor arithmetic, TS-or-SS branch per MMA) costs 16.6 instructions
 // = ~73 issue cycles per 64-cycle MMA (ncu r02a, B = 256: the elected thread was busy issuing 73 % of the time, waiting
 // for data 3 % and for the epilogue 14 %): the tensor pipe was bounded by instruction issue, not by operands.
-template <int BN, int NC, int KBS, int NKBT>
+//
+// PRE = the sampling pre-pass.  Its only product is a per-query lower bound of the kc-th best score, so it keeps no
+// candidate lists: the epilogue folds every sampled score into kPreSlots running maxima (slot = accumulator column mod 32;
+// slots partition the sampled rows, so the kc-th largest slot maximum is reached by at least kc distinct rows) with
+// straight-line FMNMX code.  r02h (ncu, 12.5 M rows): the list-based pre-pass spent 0.72 / 0.40 / 0.28 ms at B = 1024 / 256 /
+// 128 -- 5-9 % of the scan it precedes -- almost entirely in the divergent sorted-list inserts of its warm-up (each insert
+// call ~450 cycles for the whole warp, ~2 700 calls per warp); the sampled rows themselves stream in ~0.03 ms.
+template <int BN, int NC, int KBS, int NKBT, bool PRE>
 __global__ void __launch_bounds__(kThreads, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kBoxBytes = (BN / NC) * BK * 2;  // this CTA's share of one BN x 64 bf16 tile
@@ -178,9 +186,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
   if (warp >= 2) {
     // private list init
-    for (int j = 0; j < p.kc; ++j) {
-      my_s[j * BM] = -INFINITY;
-      my_i[j * BM] = -1;
+    if (!PRE) {
+      for (int j = 0; j < p.kc; ++j) {
+        my_s[j * BM] = -INFINITY;
+        my_i[j * BM] = -1;
+      }
     }
     // query tile -> TMEM: lane = query, 32-bit column c holds elements (2c, 2c+1); K blocks >= nkb_tmem go to
     // shared memory as K-major tiles in the 128-byte-swizzle canonical layout (row = query, 16-byte chunk c of the
@@ -380,6 +390,55 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         else ptx::tc_commit_pair(ptx::smem_u32(&tfull_bar[buf]), 3);
       }
     }
+  } else if (PRE) {
+    // ===================== epilogue of the pre-pass: slot maxima =====================
+    const bool live = query < p.B;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    float smax[kPreSlots];
+#pragma unroll
+    for (int j = 0; j < kPreSlots; ++j) smax[j] = -INFINITY;
+    int it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+      const int buf = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[buf]), use & 1);
+      ptx::tc_fence_after();
+      const uint32_t acc = lane_addr + (uint32_t)(p.acc_col0 + buf * BN);
+      const int64_t row0 = t * p.tstride * BN;
+      const int valid = (int)min((int64_t)BN, p.n_rows - row0);
+      // 32 columns at a time: 32 + 32 live registers instead of BN + 32 (the pre-pass has TMEM bandwidth to spare)
+#pragma unroll
+      for (int c32 = 0; c32 < BN / 32; ++c32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(acc + c32 * 32, r);
+        ptx::tmem_ld_wait();
+        if (c32 == BN / 32 - 1) {  // last read of this accumulator buffer: hand it back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (NC == 1) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[buf]));
+            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[buf]), 0));
+          }
+        }
+        if (valid == BN && !p.weight_pre) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) smax[c] = fmaxf(smax[c], __uint_as_float(r[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int cc = c32 * 32 + c;
+            float sv = __uint_as_float(r[c]);
+            if (p.weight_pre) sv *= level_weight_f((cc < valid) ? p.levels[row0 + cc] : (uint8_t)2);
+            smax[c] = fmaxf(smax[c], (cc < valid) ? sv : -INFINITY);  // rows past the end: TMA zero fill
+          }
+        }
+      }
+    }
+    if (live) {
+      float* out_s = p.part_score + ((size_t)query * p.G + g) * kPreSlots;
+#pragma unroll
+      for (int j = 0; j < kPreSlots; ++j) out_s[j] = smax[j];
+    }
   } else {
     // ===================== epilogue: fused top-k =====================
     const bool live = query < p.B;
@@ -576,7 +635,7 @@ static int env_int(const char* name, int dflt) {
 #endif
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, gen;
+  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, pre_slots, gen;
   Tunables() {
     bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
@@ -588,6 +647,7 @@ struct Tunables {
     pair = env_int("ICD_SCAN_PAIR", -1);      // CTA pairs: -1 auto (even number of query tiles >= 2), 0 off
     qtmem = env_int("ICD_SCAN_QTMEM", 0);      // K blocks of the query tile kept in TMEM when split (0 = all that fit: 8)
     tiled = 0;
+    pre_slots = 1;
     generic = env_int("ICD_SCAN_GENERIC", 0);   // 1 = always the generic (run-time shape) issue loop: A/B only
     gen = 0;
   }
@@ -612,6 +672,7 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_pair")) t.pair = value;
   else if (!strcmp(key, "scan_qtmem")) t.qtmem = std::max(0, value);
   else if (!strcmp(key, "scan_generic")) t.generic = value != 0;
+  else if (!strcmp(key, "scan_pre_slots")) t.pre_slots = value != 0;
 #ifdef ICD_PROFILING
   else if (!strcmp(key, "scan_tiled")) t.tiled = value != 0;
 #endif
@@ -622,6 +683,8 @@ int tensor_scan_tune(const char* key, int value) {
 int tensor_scan_generation() { return tun().gen; }
 
 int tensor_scan_max_partials() { return kSMs; }
+int tensor_scan_pre_slots() { return kPreSlots; }
+int tensor_scan_pre_mode() { return tun().pre_slots; }
 int tensor_scan_sample_stride(int64_t n_rows) {
   const int forced = tun().sample;
   if (forced >= 0) return forced <= 1 ? 0 : forced;
@@ -654,7 +717,7 @@ template <int BN>
 static int resident_pairs(size_t smem) {
   static int cached = 0;
   if (cached) return cached;
-  cudaFuncSetAttribute(scan_tc_kernel<BN, 2, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  cudaFuncSetAttribute(scan_tc_kernel<BN, 2, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(kSMs);
   cfg.blockDim = dim3(kThreads);
@@ -667,7 +730,7 @@ static int resident_pairs(size_t smem) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, scan_tc_kernel<BN, 2, 0, 0>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, scan_tc_kernel<BN, 2, 0, 0, false>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     n = 0;
   }
@@ -675,9 +738,9 @@ static int resident_pairs(size_t smem) {
   return cached;
 }
 
-template <int BN, int NC, int KBS, int NKBT>
-static int launch_one(const CUtensorMap& tmap, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
-  auto kernel = scan_tc_kernel<BN, NC, KBS, NKBT>;
+template <int BN, int NC, int KBS, int NKBT, bool PRE>
+static int launch_one_pre(const CUtensorMap& tmap, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+  auto kernel = scan_tc_kernel<BN, NC, KBS, NKBT, PRE>;
   static bool attr_set = false;
   if (!attr_set) {
     ICD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
@@ -700,6 +763,12 @@ static int launch_one(const CUtensorMap& tmap, const ScanParams& p, int grid, si
   ICD_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, p));
   count_launch();
   return ICD_OK;
+}
+
+template <int BN, int NC, int KBS, int NKBT>
+static int launch_one(const CUtensorMap& tmap, const ScanParams& p, int grid, size_t smem, cudaStream_t st, bool pre) {
+  return pre ? launch_one_pre<BN, NC, KBS, NKBT, true>(tmap, p, grid, smem, st)
+             : launch_one_pre<BN, NC, KBS, NKBT, false>(tmap, p, grid, smem, st);
 }
 
 template <int BN>
@@ -806,13 +875,14 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.tiled = (tun().tiled && BN == 128) ? 1 : 0;
 #endif
     // specialised issue loops for the shapes the launcher actually picks at dim = 768 (everything else: generic)
+    const bool pre = a.pre_slots != 0;
     const bool spec = BN == 128 && a.dim == 768 && nkb_tmem == 8 && tun().generic == 0;
-    if (pair && spec && kbs == 6) ICD_TRY((launch_one<BN, 2, 6, 8>(tmap, p, G * p.T, smem, st)));
-    else if (pair && spec && kbs == 3) ICD_TRY((launch_one<BN, 2, 3, 8>(tmap, p, G * p.T, smem, st)));
-    else if (pair) ICD_TRY((launch_one<BN, 2, 0, 0>(tmap, p, G * p.T, smem, st)));
-    else if (spec && kbs == 3) ICD_TRY((launch_one<BN, 1, 3, 8>(tmap, p, G * p.T, smem, st)));
-    else if (spec && kbs == 2) ICD_TRY((launch_one<BN, 1, 2, 8>(tmap, p, G * p.T, smem, st)));
-    else ICD_TRY((launch_one<BN, 1, 0, 0>(tmap, p, G * p.T, smem, st)));
+    if (pair && spec && kbs == 6) ICD_TRY((launch_one<BN, 2, 6, 8>(tmap, p, G * p.T, smem, st, pre)));
+    else if (pair && spec && kbs == 3) ICD_TRY((launch_one<BN, 2, 3, 8>(tmap, p, G * p.T, smem, st, pre)));
+    else if (pair) ICD_TRY((launch_one<BN, 2, 0, 0>(tmap, p, G * p.T, smem, st, pre)));
+    else if (spec && kbs == 3) ICD_TRY((launch_one<BN, 1, 3, 8>(tmap, p, G * p.T, smem, st, pre)));
+    else if (spec && kbs == 2) ICD_TRY((launch_one<BN, 1, 2, 8>(tmap, p, G * p.T, smem, st, pre)));
+    else ICD_TRY((launch_one<BN, 1, 0, 0>(tmap, p, G * p.T, smem, st, pre)));
   }
   return ICD_OK;
 }

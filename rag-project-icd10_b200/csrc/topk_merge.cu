@@ -75,6 +75,27 @@ merge_kernel(const float* __restrict__ part_score, const int* __restrict__ part_
   }
 }
 
+// Pre-pass bound (scan_tc.cu, PRE): lane j owns slot j; its value is the maximum of that slot over the P row groups.  Slots
+// partition the sampled rows, so the kc-th largest slot value is reached by >= kc distinct rows: a proven lower bound of the
+// kc-th best score of the table.  One warp per query.
+__global__ void __launch_bounds__(kMergeWarps * 32)
+bound_from_slots_kernel(const float* __restrict__ slot_max, int B, int P, int kc, int* __restrict__ bound_key_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kMergeWarps + warp;
+  if (b >= B) return;
+  const float* base = slot_max + (size_t)b * P * 32;
+  float m = -INFINITY;
+  for (int g = 0; g < P; ++g) m = fmaxf(m, base[(size_t)g * 32 + lane]);
+  // rank of this lane's value among the 32 (descending, ties by lane)
+  int rank = 0;
+#pragma unroll
+  for (int o = 0; o < 32; ++o) {
+    const float v = __shfl_sync(0xffffffffu, m, o);
+    rank += (v > m || (v == m && o < lane)) ? 1 : 0;
+  }
+  if (rank == kc - 1) bound_key_out[b] = (m == -INFINITY) ? (int)0x80808080 : float_key(m);
+}
+
 // canonical exact dot: chunk c of the row belongs to lane c%32, chunks ascending, elements
 // ascending, then xor-butterfly -- identical to scan_stream.cu
 template <bool F32ROWS>
@@ -278,6 +299,18 @@ int launch_merge(const MergeArgs& a, cudaStream_t st) {
   const int grid = (a.B + kMergeWarps - 1) / kMergeWarps;
   merge_kernel<<<grid, kMergeWarps * 32, 0, st>>>(a.part_score, a.part_id, a.B, a.P, a.k_in, a.k_out,
                                                  a.out_score, a.out_id, a.row_offset, a.bound_key_out);
+  count_launch();
+  ICD_CUDA(cudaGetLastError());
+  return ICD_OK;
+}
+
+int launch_bound_from_slots(const float* slot_max, int B, int P, int slots, int kc, int* bound_key_out, cudaStream_t st) {
+  if (slots != 32 || kc < 1 || kc > 32 || P < 1) {
+    set_error("bound_from_slots: slots=%d kc=%d P=%d", slots, kc, P);
+    return ICD_E_ARG;
+  }
+  const int grid = (B + kMergeWarps - 1) / kMergeWarps;
+  bound_from_slots_kernel<<<grid, kMergeWarps * 32, 0, st>>>(slot_max, B, P, kc, bound_key_out);
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;

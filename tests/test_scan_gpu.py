@@ -214,7 +214,9 @@ def test_full_size_properties(pkg, native):
 
 @pytest.mark.parametrize("knobs", [dict(scan_sample=4), dict(scan_sample=3, scan_drift=1), dict(scan_sample=0, scan_drift=0),
                                    dict(scan_sample=8, scan_tmax=2), dict(scan_sample=2, scan_kbs=2), dict(scan_kbs=6), dict(scan_kbs=4, scan_qsplit=0),
-                                   dict(scan_qsplit=0), dict(scan_qsplit=1, scan_sample=4), dict(scan_qsplit=1, scan_tmax=1)])
+                                   dict(scan_qsplit=0), dict(scan_qsplit=1, scan_sample=4), dict(scan_qsplit=1, scan_tmax=1),
+                                   dict(scan_sample=4, scan_pre_slots=0), dict(scan_sample=2, scan_pre_slots=0, scan_tmax=2),
+                                   dict(scan_sample=16, scan_pair=0), dict(scan_sample=5, scan_generic=1)])
 @pytest.mark.parametrize("weight_mode", [2, 1])
 def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
     """The sampling pre-pass (admission bound from every s-th row tile), the drift limiter and the
@@ -234,7 +236,7 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         native.tune(**knobs)
         score, raw, ids = idx.search(q, k, weight_mode=weight_mode, path=native.PATH_TENSOR)
     finally:
-        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_qsplit=-1)
+        native.tune(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_qsplit=-1, scan_pre_slots=1, scan_pair=-1, scan_generic=0)
     if weight_mode == native.WEIGHT_PRE:
         w = np.array([1.0, 1.2, 1.0, 0.8], np.float32)[levels]
         full = (q @ corpus.T) * w[None, :]
@@ -251,6 +253,27 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
         # the planted duplicates: both copies of the row come back, lower id first
         for b in range(32):
             assert ids[b, 0] == 1000 + b and ids[b, 1] == 50000 + b, (b, ids[b, :3])
+    idx.close()
+
+
+@pytest.mark.parametrize("k", [10, 26, 27, 60])
+def test_pre_pass_bound_is_valid_for_every_k(pkg, native, k):
+    """The pre-pass bound must never exceed the true kc-th best score: slot maxima for kc <= 32 (k <= 26), the list-based
+    pre-pass beyond; a tiny table with a forced stride makes slots sparse (some stay empty)."""
+    n, B, dim = 30000, 130, 768
+    corpus = _corpus(n, dim, seed=41)
+    levels = _levels(n, seed=42)
+    q = _corpus(B, dim, seed=43)
+    q[:16] = corpus[777:793]
+    idx = _index(pkg, corpus, levels)
+    try:
+        for stride in (2, 64):
+            native.tune(scan_sample=stride)
+            score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
+            ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+            check_topk(ids, raw, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    finally:
+        native.tune(scan_sample=-1)
     idx.close()
 
 
