@@ -155,7 +155,7 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
       ICD_CUDA(cudaMemsetAsync((int*)x->gbound.ptr + B, 0, (size_t)2 * prog_ints * 4, st));
       a.gbound = (int*)x->gbound.ptr;
       a.progress = (int*)x->gbound.ptr + B;
-      const int sample = tensor_scan_sample_stride(n);
+      const int sample = tensor_scan_sample_stride(n, kc);
       ICD_CUDA(cudaMemsetAsync(x->gbound.ptr, 0x80, (size_t)B * 4, st));
       if (sample > 1) {
         // sampling pre-pass over every `sample`-th row tile: a proven lower bound of the final kc-th best score per

@@ -47,8 +47,8 @@ struct TensorScanArgs {
 };
 int tensor_scan_pre_slots();
 int tensor_scan_pre_mode();   // 1 = slot-maxima pre-pass (default), 0 = list-based pre-pass (icd_tune "scan_pre_slots")
-// stride of the sampling pre-pass for a table of n_rows (0 = no pre-pass)
-int tensor_scan_sample_stride(int64_t n_rows);
+// stride of the sampling pre-pass for a table of n_rows when the scan keeps kc candidates per query (0 = no pre-pass)
+int tensor_scan_sample_stride(int64_t n_rows, int kc);
 // run-time tuning (icd_tune); the generation moves whenever a knob that shapes the TMA descriptor changes
 int tensor_scan_tune(const char* key, int value);
 int tensor_scan_generation();

@@ -685,11 +685,20 @@ int tensor_scan_generation() { return tun().gen; }
 int tensor_scan_max_partials() { return kSMs; }
 int tensor_scan_pre_slots() { return kPreSlots; }
 int tensor_scan_pre_mode() { return tun().pre_slots; }
-int tensor_scan_sample_stride(int64_t n_rows) {
+int tensor_scan_sample_stride(int64_t n_rows, int kc) {
   const int forced = tun().sample;
   if (forced >= 0) return forced <= 1 ? 0 : forced;
-  // calibrated on 10 M and 100 M rows (profiles/r01_scan_experiments.md): the optimum is broad around 256
-  return n_rows >= (2 << 20) ? 256 : (n_rows >= (1 << 19) ? 64 : 0);
+  if (kc > kPreSlots || tun().pre_slots == 0) {
+    // list-based pre-pass (its warm-up inserts cost as much as they save on small tables): calibrated in round 1
+    return n_rows >= (2 << 20) ? 256 : (n_rows >= (1 << 19) ? 64 : 0);
+  }
+  // slot-maxima pre-pass: its cost is the sampled rows' share of the stream (rows / stride), its gain the main scan's
+  // warm-up inserts (~ log of the stride), so the optimum keeps the SAMPLE at about 200 k rows whatever the table size:
+  // stride 8 at 1 M rows (0.48 vs 1.02 ms with 256), 64 at 12.5 M, 256 at 100 M (profiles/r02k_prepass_stride_ab.jsonl)
+  if (n_rows < (1 << 19)) return 0;  // below ~0.5 M rows a search is a few tens of microseconds: two more launches do not pay
+  int stride = 4;
+  while (stride < 256 && (double)n_rows / (2.0 * stride) > 141000.0) stride *= 2;  // nearest power of two to rows / 200 k
+  return stride;
 }
 int tensor_scan_progress_ints() { return 64 * kSMs; }
 
