@@ -540,12 +540,14 @@ def bench_encoder_text(dev, rank, world, min_texts=200_000):
         os.environ.setdefault("EMBEDDING_MODEL_NAME", "synthetic-text2vec-base-chinese")
         svc = S.EmbeddingService()
         svc.encode_queries(mine[:20000])                     # warm-up: allocations, thread pools
-        launches0 = N.lib().icd_launch_count()
-        t0 = time.perf_counter()
-        vecs = svc.encode_queries(mine)
-        dt = time.perf_counter() - t0
-        launches = int(N.lib().icd_launch_count() - launches0)
-        stats = dict(getattr(eng, "last_stats", {}) or {})
+        runs = []
+        for _ in range(3):                                   # three full passes; the median one is reported
+            launches0 = N.lib().icd_launch_count()
+            t0 = time.perf_counter()
+            vecs = svc.encode_queries(mine)
+            dt = time.perf_counter() - t0
+            runs.append((dt, int(N.lib().icd_launch_count() - launches0), dict(getattr(eng, "last_stats", {}) or {})))
+        dt, launches, stats = sorted(runs, key=lambda r: r[0])[1]
         ok = bool(vecs.shape == (len(mine), 768) and np.all(np.abs(np.linalg.norm(vecs, axis=1) - 1.0) < 1e-3))
         # the reference-typed call: encode_batch returns vectors.tolist() (embedding_service.py:104)
         n_b = min(len(mine), 40_000)
@@ -560,6 +562,7 @@ def bench_encoder_text(dev, rank, world, min_texts=200_000):
                 "mean_tokens": tokens / max(1, len(mine)), "host_threads": os.cpu_count(), "gpu_launches": launches,
                 "h2d_bytes": int(stats.get("h2d_bytes", 0)), "d2h_bytes": len(mine) * 768 * 4,
                 "stages_s": {k: v for k, v in stats.items() if k.endswith("_s")},
+                "all_runs_s": [r[0] for r in runs],
                 "tokenizer": stats.get("tokenizer"),
                 "encode_batch_tolist": {"value": n_b / dt_b, "unit": "sentences/s", "sentences": n_b,
                                         "note": "returns list[list[float]] like the reference; .tolist() of n x 768 "

@@ -178,7 +178,7 @@ class EncoderEngine:
         stream = f["stream"]
         chunks = [(lo, min(n, lo + FEED_CHUNK)) for lo in range(0, n, FEED_CHUNK)]
         stats = {"sentences": n, "tokens": 0, "h2d_bytes": 0, "tokenize_wait_s": 0.0, "pack_s": 0.0, "slot_wait_s": 0.0,
-                 "copy_out_s": 0.0, "batches": 0}
+                 "launch_s": 0.0, "unsort_s": 0.0, "copy_out_s": 0.0, "batches": 0}
         t_all = time.perf_counter()
         fut = f["pool"].submit(self._token_table, items[chunks[0][0]:chunks[0][1]])
         pending = None       # (chunk index, lo, hi) whose output copy is in flight
@@ -214,10 +214,12 @@ class EncoderEngine:
                     stats["slot_wait_s"] += t1 - t0
                     stats["pack_s"] += time.perf_counter() - t1
                     dt = N.F32 | (0 if normalise else 0x100)
+                    t2 = time.perf_counter()
                     N.check(N.lib().icd_encoder_forward(self._h, h_ids.ctypes.data, h_lens.ctypes.data, B, S,
                                                         d_sorted[row0:row0 + B].data_ptr(), dt,
                                                         C.c_void_p(stream.cuda_stream), 0), "icd_encoder_forward")
                     f["in_ev"][slot].record(stream)
+                    stats["launch_s"] += time.perf_counter() - t2
                     stats["h2d_bytes"] += B * S * 4 + B * 4
                     stats["batches"] += 1
                     perm[row0:row0 + B] = rows
@@ -227,6 +229,7 @@ class EncoderEngine:
                 if pending is not None and (pending[0] & 1) == (ci & 1):
                     finish(pending)
                     pending = None
+                t3 = time.perf_counter()
                 inv = f["inv"][ci & 1].numpy()           # free again: chunk ci-2 was finished an iteration ago
                 inv[perm] = np.arange(m)
                 f["d_inv"][:m].copy_(f["inv"][ci & 1][:m], non_blocking=True)
@@ -238,6 +241,7 @@ class EncoderEngine:
                     continue
                 f["out"][ci & 1][:m].copy_(d_sorted[:m].index_select(0, f["d_inv"][:m]), non_blocking=True)
                 f["out_ev"][ci & 1].record(stream)
+                stats["unsort_s"] += time.perf_counter() - t3
                 if pending is not None:
                     finish(pending)
                 pending = (ci, lo, hi)
