@@ -342,6 +342,9 @@ def test_config1_10k_queries_through_the_service_api(tmp_path, monkeypatch):
     q /= np.linalg.norm(q, axis=1, keepdims=True)
     ms.search_batch(q[:64], top_k=10)
     t0 = time.perf_counter()
+    got = ms.search_batch(q, top_k=10)          # first call at this batch size: workspace allocation, kernel loading
+    dt_first = time.perf_counter() - t0
+    t0 = time.perf_counter()
     got = ms.search_batch(q, top_k=10)
     dt = time.perf_counter() - t0
     assert len(got) == nq and all(len(c) == 10 for c in got[:50])
@@ -362,7 +365,7 @@ def test_config1_10k_queries_through_the_service_api(tmp_path, monkeypatch):
           f"materialising all {n_dicts} hit dicts: {dt_dicts * 1e3:.0f} ms")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "r02_config1.json"), "w") as fh:
-        json.dump({"queries": nq, "rows": len(recs), "search_batch_ms": dt * 1e3, "queries_per_s": nq / dt,
+        json.dump({"queries": nq, "rows": len(recs), "search_batch_ms": dt * 1e3, "first_call_ms": dt_first * 1e3, "queries_per_s": nq / dt,
                    "materialise_all_hit_dicts_ms": dt_dicts * 1e3, "hit_dicts": n_dicts}, fh)
     assert dt < 2.0
     ms.disconnect()
