@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence, Union
@@ -45,6 +46,9 @@ class EncoderEngine:
         self.vocab_path = vocab_path
         self.last_stats: dict = {}
         self._feed = None          # pinned staging buffers, created on first bulk encode
+        # one in-flight call per native handle (include/icdrag.h): the reference serves requests from a thread pool
+        # (FastAPI sync endpoints), and ctypes releases the GIL during a call
+        self._lock = threading.RLock()
         # host feeder: multi-threaded WordPiece in libicdrag for plain BERT tokenizers, the tokenizer itself otherwise
         self._ntok = NativeTokenizer(tokenizer, threads=host_threads) if hasattr(tokenizer, "backend_tokenizer") else None
         self._h = C.c_void_p()
@@ -139,7 +143,8 @@ class EncoderEngine:
                                "encode_s": time.perf_counter() - t1, "h2d_bytes": int(lens.sum()) * 4,
                                "tokenizer": self._tokenizer_kind()}
             return out
-        return self._encode_pipelined(items, normalise, to_device)
+        with self._lock:     # the pipeline owns the pinned slots and the stream for its whole duration
+            return self._encode_pipelined(items, normalise, to_device)
 
     def _tokenizer_kind(self) -> str:
         if self._ntok is not None and self._ntok.native:
@@ -264,8 +269,9 @@ class EncoderEngine:
             else:
                 out = np.empty((B, self.cfg.hidden), np.float32)
         dt = N.vec_dtype(out) | (0 if normalise else 0x100)
-        N.check(N.lib().icd_encoder_forward(self._h, N.buf_ptr(ids), N.buf_ptr(lens), B, S, N.buf_ptr(out), dt,
-                                            C.c_void_p(stream), 1 if sync else 0), "icd_encoder_forward")
+        with self._lock:
+            N.check(N.lib().icd_encoder_forward(self._h, N.buf_ptr(ids), N.buf_ptr(lens), B, S, N.buf_ptr(out), dt,
+                                                C.c_void_p(stream), 1 if sync else 0), "icd_encoder_forward")
         return out
 
     def set_token_head(self, weight: np.ndarray, bias: np.ndarray) -> None:
@@ -290,8 +296,9 @@ class EncoderEngine:
                 out = torch.empty((B, S, L), dtype=torch.float32, device=ids.device)
             else:
                 out = np.empty((B, S, L), np.float32)
-        N.check(N.lib().icd_encoder_token_logits(self._h, N.buf_ptr(ids), N.buf_ptr(lens), B, S, N.buf_ptr(out),
-                                                 C.c_void_p(stream), 1 if sync else 0), "icd_encoder_token_logits")
+        with self._lock:
+            N.check(N.lib().icd_encoder_token_logits(self._h, N.buf_ptr(ids), N.buf_ptr(lens), B, S, N.buf_ptr(out),
+                                                     C.c_void_p(stream), 1 if sync else 0), "icd_encoder_token_logits")
         return out
 
     def read_hidden(self, tokens: int) -> np.ndarray:

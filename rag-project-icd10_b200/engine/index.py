@@ -7,6 +7,7 @@ All arithmetic happens in libicdrag.so on the GPU; this class only moves pointer
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Tuple
 
 import numpy as np
@@ -23,6 +24,7 @@ class VectorIndex:
                                          N.INDEX_KEEP_F32 if keep_f32 else 0, C.byref(self._h)),
                 "icd_index_create")
         self._adopted = None  # keeps adopted tensors alive
+        self._lock = threading.RLock()   # one in-flight call per handle (the workspace is per handle); ctypes drops the GIL
 
     # ---------------------------------------------------------------- lifetime
     def close(self) -> None:
@@ -53,8 +55,9 @@ class VectorIndex:
                 raise ValueError("levels length mismatch")
             if N._is_torch(levels) != N._is_torch(vecs) or (N._is_torch(vecs) and levels.device != vecs.device):
                 raise ValueError("vecs and levels must live in the same memory space")
-        N.check(N.lib().icd_index_append(self._h, N.buf_ptr(vecs), N.vec_dtype(vecs), N.buf_ptr(levels), n),
-                "icd_index_append")
+        with self._lock:
+            N.check(N.lib().icd_index_append(self._h, N.buf_ptr(vecs), N.vec_dtype(vecs), N.buf_ptr(levels), n),
+                    "icd_index_append")
 
     def adopt(self, table_bf16, levels_u8) -> None:
         """Zero-copy: scan caller-owned device tensors ([n, dim] bfloat16, [n] uint8)."""
@@ -68,7 +71,8 @@ class VectorIndex:
 
     def read(self, row0: int, n: int) -> np.ndarray:
         out = np.empty((n, self.dim), np.float32)
-        N.check(N.lib().icd_index_read(self._h, int(row0), int(n), N.buf_ptr(out)), "icd_index_read")
+        with self._lock:
+            N.check(N.lib().icd_index_read(self._h, int(row0), int(n), N.buf_ptr(out)), "icd_index_read")
         return out
 
     # ---------------------------------------------------------------- search
@@ -95,9 +99,10 @@ class VectorIndex:
                 ids = np.empty((B, k), np.int64)
         else:
             score, raw, ids = out
-        N.check(N.lib().icd_index_search(self._h, N.buf_ptr(q), N.vec_dtype(q), B, int(k), int(weight_mode),
-                                         int(path), N.buf_ptr(score), N.buf_ptr(raw), N.buf_ptr(ids),
-                                         C.c_void_p(stream), 1 if sync else 0), "icd_index_search")
+        with self._lock:
+            N.check(N.lib().icd_index_search(self._h, N.buf_ptr(q), N.vec_dtype(q), B, int(k), int(weight_mode),
+                                             int(path), N.buf_ptr(score), N.buf_ptr(raw), N.buf_ptr(ids),
+                                             C.c_void_p(stream), 1 if sync else 0), "icd_index_search")
         return score, raw, ids
 
     def set_timing(self, on: bool) -> None:

@@ -54,10 +54,11 @@ class ShardGroup:
             else:
                 out = (np.empty((B, k), np.float32), np.empty((B, k), np.float32), np.empty((B, k), np.int64))
         score, raw, ids = out
-        N.check(N.lib().icd_shard_group_search(self._h, N.buf_ptr(q), N.vec_dtype(q), B, int(k), int(weight_mode),
-                                               int(path), int(exchange), N.buf_ptr(score), N.buf_ptr(raw),
-                                               N.buf_ptr(ids), C.c_void_p(stream), 1 if sync else 0),
-                "icd_shard_group_search")
+        with self.index._lock:       # the group searches through the local index's workspace
+            N.check(N.lib().icd_shard_group_search(self._h, N.buf_ptr(q), N.vec_dtype(q), B, int(k), int(weight_mode),
+                                                   int(path), int(exchange), N.buf_ptr(score), N.buf_ptr(raw),
+                                                   N.buf_ptr(ids), C.c_void_p(stream), 1 if sync else 0),
+                    "icd_shard_group_search")
         return score, raw, ids
 
     def close(self) -> None:

@@ -369,3 +369,35 @@ def test_config1_10k_queries_through_the_service_api(tmp_path, monkeypatch):
                    "materialise_all_hit_dicts_ms": dt_dicts * 1e3, "hit_dicts": n_dicts}, fh)
     assert dt < 2.0
     ms.disconnect()
+
+
+def test_services_are_safe_under_a_request_thread_pool(tmp_path, monkeypatch, model_dir):
+    """The reference serves requests from a thread pool (FastAPI sync endpoints, main.py); ctypes drops the GIL during a
+    native call, so two requests can reach one engine at once.  Every engine handle is guarded by a lock: concurrent
+    encode_query + search give exactly the single-threaded answers."""
+    from concurrent.futures import ThreadPoolExecutor
+    d, state = model_dir
+    src = open(os.path.join(ROOT, "data", "ICD_10v601.csv"), encoding="utf-8-sig").read().splitlines()
+    sub_csv = tmp_path / "subset.csv"
+    sub_csv.write_text("﻿" + "\n".join(src[:801]) + "\n", encoding="utf-8")
+    monkeypatch.setenv("EMBEDDING_MODEL_NAME", d)
+    monkeypatch.setenv("MILVUS_DB_PATH", str(tmp_path / "db" / "icd.db"))
+    monkeypatch.setenv("MILVUS_COLLECTION_NAME", "icd10")
+    monkeypatch.chdir(tmp_path)
+    B = importlib.import_module("rag-project-icd10_b200.tools.build_database")
+    builder = B.DatabaseBuilder()
+    assert builder.build_full_database(str(sub_csv), rebuild=True)
+    es, ms = builder.embedding_service, builder.milvus_service
+    recs = otext.load_records(str(sub_csv))
+    probes = [r["preferred_zh"] for r in recs[::16]][:48]
+    want = [ms.search(es.encode_query(p), top_k=5) for p in probes]
+
+    def one(i):
+        p = probes[i % len(probes)]
+        return i % len(probes), ms.search(es.encode_query(p), top_k=5)
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        got = list(pool.map(one, range(6 * len(probes))))
+    for i, hits in got:
+        assert [h["code"] for h in hits] == [h["code"] for h in want[i]]
+        assert all(abs(a["original_score"] - b["original_score"]) < 1e-6 for a, b in zip(hits, want[i]))
+    ms.disconnect()
