@@ -3,6 +3,8 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench as E
+import importlib as _il
+_il.import_module("rag-project-icd10_b200._native").tune(enc_pdl=int(os.environ.get("ENC_PDL", "0")))
 B, S = int(os.environ.get("ENC_B", 4096)), int(os.environ.get("ENC_S", 64))
 reps = int(os.environ.get("ENC_REPS", 20))
 eng = E.synthetic_engine(device=0, max_tokens=B * S)

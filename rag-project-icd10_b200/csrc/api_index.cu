@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "index_impl.h"
 #include "kernels.h"
+#include "encoder_kernels.h"
 
 namespace icd {
 
@@ -295,6 +296,10 @@ const char* icd_last_error(void) { return t_error.c_str(); }
 int64_t icd_launch_count(void) { return g_launches.load(); }
 int icd_tune(const char* key, int value) {
   ICD_CHECK_ARG(key != nullptr, "key is null");
+  if (!strcmp(key, "enc_pdl")) {
+    encoder_set_pdl(value);
+    return ICD_OK;
+  }
   if (tensor_scan_tune(key, value) != ICD_OK) {
     set_error("icd_tune: unknown key '%s'", key);
     return ICD_E_ARG;

@@ -114,6 +114,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // barriers and tensor memory are set up: let the next kernel of the forward start its own prologue, then wait for the
+  // QKV projection to have completed before the first load
+  ptx::griddep_launch();
+  ptx::griddep_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -382,9 +386,8 @@ int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S,
   memcpy(&tc, ctx_map, sizeof(tc));
   ICD_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int grid = std::min(p.tiles * kHeads, kSMs);
-  attention_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(tm, tc, p);
+  ICD_CUDA(launch_chained(attention_tc_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, st, 1, tm, tc, p));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 

@@ -5,6 +5,7 @@
 // Hidden size is 768 (24 elements per lane with a warp per token), heads of 64.
 #include "common.cuh"
 #include "encoder_kernels.h"
+#include "ptx.cuh"
 
 namespace icd {
 namespace {
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ ids, int M, int S, int vocab, int unk, const float* __restrict__ word,
                 const float* __restrict__ pos, const float* __restrict__ type0, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();   // `out` is read by kernels of the previous forward that may still be running
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * 8 + warp;
   if (tok >= M) return;
@@ -83,6 +86,8 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int M, int S, int vocab, int un
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ in, int M, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok = blockIdx.x * 8 + warp;
   if (tok >= M) return;
@@ -114,6 +119,8 @@ constexpr int kLongMaxS = 512;
 __global__ void __launch_bounds__(128)
 attention_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
                       __nv_bfloat16* __restrict__ ctx) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   extern __shared__ __align__(16) unsigned char sm_raw[];
   uint4* Ks = reinterpret_cast<uint4*>(sm_raw);   // [len][8] uint4 = [len][64] bf16
   const int b = blockIdx.x, h = blockIdx.y;
@@ -209,6 +216,8 @@ attention_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
 __global__ void __launch_bounds__(256)
 pool_normalise_kernel(const __nv_bfloat16* __restrict__ h, const int32_t* __restrict__ lens, int S,
                       void* __restrict__ out, int out_dtype, int normalise) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   __shared__ float red[8];
   const int b = blockIdx.x;
   const int len = min(lens[b], S);
@@ -250,6 +259,8 @@ pool_normalise_kernel(const __nv_bfloat16* __restrict__ h, const int32_t* __rest
 __global__ void __launch_bounds__(256)
 token_head_kernel(const __nv_bfloat16* __restrict__ h, int M, const float* __restrict__ w,
                   const float* __restrict__ b, int L, float* __restrict__ out) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + warp;
   if (m >= M) return;
@@ -269,29 +280,31 @@ token_head_kernel(const __nv_bfloat16* __restrict__ h, int M, const float* __res
 
 }  // namespace
 
+static int g_encoder_pdl = 0;  // flipped to 1 once validated on the GPU (r02o)
+int encoder_pdl() { return g_encoder_pdl; }
+void encoder_set_pdl(int on) { g_encoder_pdl = on ? 1 : 0; }
+
 int launch_token_head(const void* h, int M, const float* w, const float* b, int L, float* out, cudaStream_t st) {
   if (M <= 0) return ICD_OK;
-  token_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h), M, w, b, L, out);
+  ICD_CUDA(launch_chained(token_head_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(h), M, w,
+                          b, L, out));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 
 int launch_embed_ln(const int32_t* ids, int M, int S, int vocab, int unk, const float* word, const float* pos,
                     const float* type0, const float* gamma, const float* beta, float eps, void* out, cudaStream_t st) {
-  embed_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(ids, M, S, vocab, unk, word, pos, type0, gamma, beta, eps,
-                                              reinterpret_cast<__nv_bfloat16*>(out));
+  ICD_CUDA(launch_chained(embed_ln_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, ids, M, S, vocab, unk, word, pos, type0, gamma, beta,
+                          eps, reinterpret_cast<__nv_bfloat16*>(out)));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 
 int launch_layernorm(const void* x, int M, const float* gamma, const float* beta, float eps, void* out,
                      cudaStream_t st) {
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, gamma, beta, eps,
-                                               reinterpret_cast<__nv_bfloat16*>(out));
+  ICD_CUDA(launch_chained(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(x), M, gamma,
+                          beta, eps, reinterpret_cast<__nv_bfloat16*>(out)));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 
@@ -306,19 +319,17 @@ int launch_attention_long(const void* qkv, const int32_t* lens, int B, int S, vo
     ICD_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kLongMaxS * HD * 2));
     attr_set = true;
   }
-  attention_long_kernel<<<dim3(B, 12, (S + 127) / 128), 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), lens, S,
-                                                                        reinterpret_cast<__nv_bfloat16*>(ctx));
+  ICD_CUDA(launch_chained(attention_long_kernel, dim3(B, 12, (S + 127) / 128), dim3(128), smem, st, 1,
+                          reinterpret_cast<const __nv_bfloat16*>(qkv), lens, S, reinterpret_cast<__nv_bfloat16*>(ctx)));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 
 int launch_pool_normalise(const void* h, const int32_t* lens, int B, int S, void* out, int out_dtype,
                           cudaStream_t st) {
-  pool_normalise_kernel<<<B, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(h), lens, S, out,
-                                           out_dtype & 0xff, (out_dtype & ICD_OUT_NO_NORMALISE) ? 0 : 1);
+  ICD_CUDA(launch_chained(pool_normalise_kernel, dim3(B), dim3(256), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(h), lens, S, out,
+                          out_dtype & 0xff, (out_dtype & ICD_OUT_NO_NORMALISE) ? 0 : 1));
   count_launch();
-  ICD_CUDA(cudaGetLastError());
   return ICD_OK;
 }
 

@@ -5,6 +5,40 @@
 
 namespace icd {
 
+// 1 (default): the kernels of one encoder forward are chained with programmatic dependent launch, so that the prologue of
+// kernel i+1 overlaps the tail of kernel i (what a batch-1 forward of 63 small launches is made of); icd_tune("enc_pdl", 0)
+// restores plain stream order.  Results never depend on it.
+int encoder_pdl();
+void encoder_set_pdl(int on);
+
+// cudaLaunchKernelEx with the programmatic-stream-serialization attribute (plus a cluster of `cluster` CTAs when > 1)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (encoder_pdl()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 enum GemmEpilogue { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_BIAS_RESIDUAL = 2 };
 
 // ---- gemm_tc.cu : out[M,N] = epi(A[M,K] * W[N,K]^T + bias)

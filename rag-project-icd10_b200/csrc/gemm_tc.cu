@@ -179,6 +179,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (NC == 2) ptx::cluster_sync(); else __syncthreads();  // barriers of BOTH CTAs are initialised from here on
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // prologue done: the next kernel of the forward may start its own; A, the residual and the LayerNorm statistics are
+  // outputs of the previous kernel, so nothing is loaded before it has completed
+  ptx::griddep_launch();
+  ptx::griddep_wait();
 
   if (warp == 0) {
     if (ptx::elect_one()) {
@@ -460,32 +464,30 @@ static int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   auto kernel = gemm_tc_kernel<NC, EPI, LNIN, STATS>;
   ICD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int tiles = ((p.M + BM * NC - 1) / (BM * NC)) * (p.N / BN);
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   int units = kSMs / NC;
   if (NC == 2) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
     // persistent kernel: as many pairs as the device can keep resident at once (a TPC with one SM fused off
     // cannot host a pair)
     static int resident = 0;
     if (resident == 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = kSmemBytes;
       cfg.gridDim = dim3(kSMs);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
       int n = 0;
       ICD_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
       resident = std::max(1, n);
     }
     units = std::min(units, resident);
   }
-  cfg.gridDim = dim3(std::min(tiles, units) * NC);
-  ICD_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, tout, tres, p));
+  ICD_CUDA(launch_chained(kernel, dim3(std::min(tiles, units) * NC), dim3(kThreads), (size_t)kSmemBytes, st, NC, ta, tb, tout, tres, p));
   count_launch();
   return ICD_OK;
 }

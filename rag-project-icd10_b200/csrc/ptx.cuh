@@ -24,6 +24,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: everything before griddep_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+// predecessor's tail; griddep_wait() returns when the predecessor has COMPLETED and its writes are visible.
+// griddep_launch() lets the successor start as soon as every CTA of this grid has called it (or exited).  Both are no-ops
+// for a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

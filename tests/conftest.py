@@ -18,6 +18,19 @@ def pkg():
     return importlib.import_module("rag-project-icd10_b200")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _encoder_pdl_from_env():
+    """ICD_TEST_ENC_PDL=0|1 runs the GPU suite with programmatic dependent launch forced off / on (default: the library's)."""
+    v = os.environ.get("ICD_TEST_ENC_PDL")
+    if v is not None and os.path.exists(os.path.join(ROOT, "rag-project-icd10_b200", "csrc", "libicdrag.so")):
+        native = importlib.import_module("rag-project-icd10_b200._native")
+        try:
+            native.tune(enc_pdl=int(v))
+        except Exception:
+            pass
+    yield
+
+
 @pytest.fixture(scope="session")
 def native(pkg):
     return importlib.import_module("rag-project-icd10_b200._native")
