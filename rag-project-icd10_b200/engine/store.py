@@ -271,6 +271,7 @@ class ColumnTable:
 
     def open(self, rows: int) -> None:
         self.n = int(rows)
+        self.__dict__.pop("_row_cache", None)
         self.f32.open(rows * self.dim)
         self.bf16.open(rows * self.dim)
         self.levels.open(rows)
@@ -296,6 +297,19 @@ class ColumnTable:
             row[f] = bool(c.view()[i])
         for f, c in self.ints.items():
             row[f] = int(c.view()[i])
+        return row
+
+    _ROW_CACHE_MAX = 131072
+
+    def cached_row(self, i: int) -> Dict[str, Any]:
+        """Decoded row i, memoised: rows are immutable once committed and a serving process returns the same few thousand
+        ICD rows over and over (9 field decodes per hit otherwise).  Callers must not mutate the dict."""
+        cache = self.__dict__.setdefault("_row_cache", {})
+        row = cache.get(i)
+        if row is None:
+            if len(cache) >= self._ROW_CACHE_MAX:
+                cache.clear()
+            row = cache[i] = self[i]
         return row
 
     def field(self, name: str, i: int):
@@ -658,7 +672,8 @@ class IcdStoreClient:
                 if j < 0:
                     break
                 g = int(j) + base
-                hits.append(Hit(id=g, distance=float(s), entity={f: col.rows.field(f, g) for f in fields}))
+                row = col.rows.cached_row(g)
+                hits.append(Hit(id=g, distance=float(s), entity={f: row.get(f) for f in fields}))
             out.append(hits)
         return out
 
@@ -684,7 +699,7 @@ class IcdStoreClient:
         return self.cols[collection_name].rows[row_id]
 
     def field(self, collection_name: str, name: str, row_id: int):
-        return self.cols[collection_name].rows.field(name, int(row_id))
+        return self.cols[collection_name].rows.cached_row(int(row_id)).get(name)
 
     def close(self) -> None:
         for col in self.cols.values():
