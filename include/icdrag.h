@@ -170,9 +170,9 @@ int icd_encoder_create(const float* weights, int64_t count, const icd_bert_cfg* 
 int icd_encoder_destroy(icd_encoder* enc);
 /* ids [B, S] int32 (0-padded), lens [B] int32 = number of real tokens (attention mask is
  * position < len); out [B, hidden] of out_dtype. S <= 512 (BERT's position table): S <= 128 -- the
- * sentence-transformers max_seq_length of text2vec-base-chinese -- runs the tensor-core attention
- * kernel, longer sequences (the token-classification path) a shared-memory one. B*S <= the
- * capacity given to icd_encoder_reserve. */
+ * sentence-transformers max_seq_length of text2vec-base-chinese -- is one tile of the tensor-core
+ * attention kernel; longer sequences (the token-classification path) run the same kernel split over
+ * 128-key tiles plus a combine pass. B*S <= the capacity given to icd_encoder_reserve. */
 int icd_encoder_reserve(icd_encoder* enc, int max_tokens);
 int icd_encoder_forward(icd_encoder* enc, const int32_t* ids, const int32_t* lens, int B, int S,
                         void* out, int out_dtype, void* stream, int sync);

@@ -69,6 +69,9 @@ struct icd_encoder {
   int ids_cap = 0, lens_cap = 0;
   void* out_stage = nullptr;
   size_t out_cap = 0;
+  // scratch of the split-KV attention (sequences beyond 128 tokens): partial outputs and row statistics
+  void *att_part = nullptr, *att_stats = nullptr;
+  size_t att_part_cap = 0, att_stats_cap = 0;
   int last_M = 0;
   // token-classification head (icd_encoder_set_token_head): logits = h W^T + b per token
   float *head_w = nullptr, *head_b = nullptr;
@@ -311,7 +314,7 @@ int icd_encoder_destroy(icd_encoder* e) {
   for (void* p : e->allocs) cudaFree(p);
   for (auto* L : e->layers) delete L;
   void* bufs[] = {e->h, e->h1, e->t, e->ctx, e->qkv, e->f, e->ids, e->lens, e->out_stage, e->stats1, e->stats2,
-                  e->head_w, e->head_b};
+                  e->head_w, e->head_b, e->att_part, e->att_stats};
   for (void* p : bufs)
     if (p) cudaFree(p);
   delete e;
@@ -363,9 +366,25 @@ static int encode_hidden(icd_encoder* e, const int32_t* ids, const int32_t* lens
   // ids outside the embedding table read [UNK] (100 in BERT vocabularies) instead of faulting
   const int unk = e->cfg.vocab_size > 100 ? 100 : 0;
   ICD_TRY(launch_embed_ln(d_ids, M, S, e->cfg.vocab_size, unk, e->word, e->pos, e->type, e->eg, e->eb, eps, e->h, st));
+  if (S > 128) {
+    size_t stats_bytes = 0;
+    const size_t part_bytes = attention_long_scratch_bytes(B, S, &stats_bytes);
+    if (part_bytes > e->att_part_cap) {
+      if (e->att_part) cudaFree(e->att_part);
+      e->att_part = nullptr, e->att_part_cap = 0;
+      ICD_CUDA(cudaMalloc(&e->att_part, part_bytes));
+      e->att_part_cap = part_bytes;
+    }
+    if (stats_bytes > e->att_stats_cap) {
+      if (e->att_stats) cudaFree(e->att_stats);
+      e->att_stats = nullptr, e->att_stats_cap = 0;
+      ICD_CUDA(cudaMalloc(&e->att_stats, stats_bytes));
+      e->att_stats_cap = stats_bytes;
+    }
+  }
   auto attention = [&]() {
     return S <= 128 ? launch_attention_tc(e->m_qkv, d_lens, B, S, e->ctx, e->max_tokens, st)
-                    : launch_attention_long(e->qkv, d_lens, B, S, e->ctx, st);
+                    : launch_attention_tc_long(e->m_qkv, d_lens, B, S, e->att_part, e->att_stats, e->ctx, st);
   };
   const void* final_h = e->h;
   if (e->fused_ln) {

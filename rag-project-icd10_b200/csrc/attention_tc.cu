@@ -26,6 +26,12 @@
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
 // warps 2..5 / 6..9 softmax warpgroups 0 / 1 (TMEM lane quarter = warp % 4).
 //
+// Sequences of 129 .. 512 tokens (the token-classification path) run the SAME kernel in split-KV mode: a work item is
+// (sequence, head, 128-query tile, 128-key tile); the softmax of an item is local to its key tile, the item stores its
+// normalised partial output as bf16 into a [key tile][padded row][768] buffer plus (row max in the log2 domain, row
+// sum) per (key tile, head, row), and attention_combine_kernel merges the <= 4 partials of a row with the weights
+// exp2(m_t - m) sum_t -- the flash-decoding split, so no kernel keeps a running max across tiles.
+//
 // Roofline: HBM (reads the 2304-wide qkv rows once, writes ctx once); the math is ~1 % of a layer.
 #include <stdlib.h>
 #include <string.h>
@@ -54,6 +60,10 @@ constexpr int kSmemBytes = kSlots * kSlotBytes + 2 * kTileBytes /*ctx staging, o
 struct AttParams {
   const int32_t* lens;
   int B, S, G, tiles;
+  // split-KV mode (S > 128): QT = ceil(S / 128) query / key tiles per sequence, S_pad = QT * 128 rows per sequence in the
+  // partial buffers, part_stats [QT][heads][B * S_pad] (log2-domain row max, row sum)
+  int QT, S_pad;
+  float2* part_stats;
 #ifdef ICD_PROFILING
   int dbg;  // ICD_ATTN_DBG (profiling builds only): 1 = skip the ctx stores, 2 = every item loads tile 0 (L2 hits)
 #endif
@@ -130,14 +140,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #else
         const int row0 = tile * p.G * p.S;
 #endif
+        int q_row0 = row0, k_row0 = row0;
+        if (p.QT > 0) {  // split-KV: tile = (sequence, query tile, key tile)
+          const int seq = tile / (p.QT * p.QT), qt = (tile / p.QT) % p.QT, kt = tile % p.QT;
+          q_row0 = seq * p.S + qt * kTile;
+          k_row0 = seq * p.S + kt * kTile;
+        }
         const int slot = j % kSlots;
         ptx::mbar_wait(ptx::smem_u32(&empty_bar[slot]), ((j / kSlots) & 1) ^ 1);
         const uint32_t fb = ptx::smem_u32(&full_bar[slot]);
         ptx::mbar_expect_tx(fb, kSlotBytes);
         const uint32_t dst = ptx::smem_u32(smem + (size_t)slot * kSlotBytes);
-        ptx::tma_load_2d(dst, &tmap_qkv, fb, head * HD, row0);
-        ptx::tma_load_2d(dst + kTileBytes, &tmap_qkv, fb, H + head * HD, row0);
-        ptx::tma_load_2d(dst + 2 * kTileBytes, &tmap_qkv, fb, 2 * H + head * HD, row0);
+        ptx::tma_load_2d(dst, &tmap_qkv, fb, head * HD, q_row0);
+        ptx::tma_load_2d(dst + kTileBytes, &tmap_qkv, fb, H + head * HD, k_row0);
+        ptx::tma_load_2d(dst + 2 * kTileBytes, &tmap_qkv, fb, 2 * H + head * HD, k_row0);
       }
     }
   } else if (warp == 1) {
@@ -186,7 +202,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int quarter = warp & 3;
     const int r = 32 * quarter + lane;  // row of the tile == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    const int g = r / p.S;
+    const int g = p.QT > 0 ? 0 : r / p.S;
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e): softmax in base 2
     const uint32_t s_addr = lane_addr + (uint32_t)(wg * kTile);  // this warpgroup's S region; P = its first 64 columns
     // epilogue of an earlier item: O from TMEM, scale by 1 / row sum, bf16 into the warpgroup's staging box
@@ -236,7 +252,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     // the sequence length of this row for item j, requested one item ahead
     auto load_len = [&](int j) {
       const int item = (int)blockIdx.x + j * (int)gridDim.x;
-      const int seq = (item / kHeads) * p.G + g;
+      const int seq = p.QT > 0 ? (item / kHeads) / (p.QT * p.QT) : (item / kHeads) * p.G + g;
       return (j < n_local && g < p.G && seq < p.B) ? __ldg(p.lens + seq) : 0;
     };
     int next_len = load_len(wg);
@@ -244,12 +260,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const int item = (int)blockIdx.x + j * (int)gridDim.x;
       const int tile = item / kHeads, head = item % kHeads;
       const uint32_t par = (uint32_t)(j >> 1) & 1;
-      const int seq = tile * p.G + g;
+      const int seq = p.QT > 0 ? tile / (p.QT * p.QT) : tile * p.G + g;
+      const int qt = p.QT > 0 ? (tile / p.QT) % p.QT : 0, kt = p.QT > 0 ? tile % p.QT : 0;
       const bool row_used = g < p.G && seq < p.B;
       const int len = row_used ? min(next_len, p.S) : 0;
       next_len = load_len(j + 2);
-      const int lo = g * p.S, hi = lo + len;  // key columns this row attends to
-      const bool q_live = row_used && (r - lo) < len;
+      // key columns this row attends to: its own sequence inside a packed tile, or (split-KV) what the key tile holds
+      const int lo = p.QT > 0 ? 0 : g * p.S;
+      const int hi = p.QT > 0 ? max(0, min(kTile, len - kt * kTile)) : lo + len;
+      const bool q_live = row_used && (p.QT > 0 ? (qt * kTile + r) < len : (r - lo) < len);
       // warp-uniform view of the key range: a 32-column chunk is `live` if some row of the warp needs it and
       // `full` if every row needs all of it (then no per-element mask: the common case of unpadded sequences)
       const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
@@ -339,6 +358,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       // padded query positions are never read downstream (masked keys, masked pooling): zeros
       prev_inv = (q_live && sum > 0.f) ? 1.0f / sum : 0.f;
       prev_row0 = tile * p.G * p.S;
+      if (p.QT > 0) {
+        // partial of (query tile, key tile): rows of key tile kt start at kt * B * S_pad in the partial buffers
+        const int prow = seq * p.S_pad + qt * kTile;
+        prev_row0 = kt * p.B * p.S_pad + prow;
+        p.part_stats[((size_t)kt * kHeads + head) * ((size_t)p.B * p.S_pad) + prow + r] =
+            make_float2(msc, (q_live && sum > 0.f) ? sum : 0.f);
+      }
       prev_head = head;
     }
     if (prev >= 0) epilogue(prev, prev_inv, prev_row0, prev_head);
@@ -351,6 +377,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// merges the <= 4 key-tile partials of every (token, head): out = sum_t w_t O_t / sum_t w_t, w_t = exp2(m_t - max m) sum_t.
+// One thread per (token, head, 8-column chunk); rows are read / written 16 bytes at a time.
+__global__ void __launch_bounds__(96)
+attention_combine_kernel(const __nv_bfloat16* __restrict__ part, const float2* __restrict__ stats, int B, int S, int S_pad,
+                         int QT, __nv_bfloat16* __restrict__ ctx) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
+  const int row = blockIdx.x;            // token row of the [B * S, 768] ctx buffer
+  const int seq = row / S, t = row % S;
+  const int head = threadIdx.x >> 3, chunk = threadIdx.x & 7;
+  const size_t prow = (size_t)seq * S_pad + t;
+  const size_t plane = (size_t)B * S_pad;
+  float m = -INFINITY;
+  float2 st[4];
+  for (int kt = 0; kt < QT; ++kt) {
+    st[kt] = stats[((size_t)kt * kHeads + head) * plane + prow];
+    if (st[kt].y > 0.f) m = fmaxf(m, st[kt].x);
+  }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f;
+  for (int kt = 0; kt < QT; ++kt) {
+    if (!(st[kt].y > 0.f)) continue;
+    const float w = ex2_approx(st[kt].x - m) * st[kt].y;
+    wsum += w;
+    const uint4 v = *reinterpret_cast<const uint4*>(part + ((size_t)kt * plane + prow) * H + head * HD + chunk * 8);
+    acc[0] = fmaf(w, bf16lo_to_f32(v.x), acc[0]); acc[1] = fmaf(w, bf16hi_to_f32(v.x), acc[1]);
+    acc[2] = fmaf(w, bf16lo_to_f32(v.y), acc[2]); acc[3] = fmaf(w, bf16hi_to_f32(v.y), acc[3]);
+    acc[4] = fmaf(w, bf16lo_to_f32(v.z), acc[4]); acc[5] = fmaf(w, bf16hi_to_f32(v.z), acc[5]);
+    acc[6] = fmaf(w, bf16lo_to_f32(v.w), acc[6]); acc[7] = fmaf(w, bf16hi_to_f32(v.w), acc[7]);
+  }
+  const float inv = wsum > 0.f ? 1.0f / wsum : 0.f;
+  uint4 o;
+  o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+  o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+  o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(ctx + (size_t)row * H + head * HD + chunk * 8) = o;
 }
 
 }  // namespace
@@ -387,6 +452,45 @@ int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S,
   ICD_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int grid = std::min(p.tiles * kHeads, kSMs);
   ICD_CUDA(launch_chained(attention_tc_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, st, 1, tm, tc, p));
+  count_launch();
+  return ICD_OK;
+}
+
+// split-KV form for 128 < S <= 512: part [QT * B * S_pad, 768] bf16 and stats [QT * 12 * B * S_pad] float2 are scratch
+size_t attention_long_scratch_bytes(int B, int S, size_t* stats_bytes) {
+  const int QT = (S + kTile - 1) / kTile;
+  const size_t rows = (size_t)QT * B * QT * kTile;
+  if (stats_bytes) *stats_bytes = (size_t)QT * kHeads * B * QT * kTile * sizeof(float2);
+  return rows * H * 2;
+}
+
+int launch_attention_tc_long(const void* tmap_qkv, const int32_t* lens, int B, int S, void* part, void* stats, void* ctx,
+                             cudaStream_t st) {
+  if (S <= kTile || S > 4 * kTile) {
+    set_error("attention (split-KV): S=%d outside (128, 512]", S);
+    return ICD_E_UNSUPPORTED;
+  }
+  AttParams p{};
+  p.lens = lens;
+  p.B = B;
+  p.S = S;
+  p.G = 1;
+  p.QT = (S + kTile - 1) / kTile;
+  p.S_pad = p.QT * kTile;
+  p.tiles = B * p.QT * p.QT;
+  p.part_stats = reinterpret_cast<float2*>(stats);
+  CUtensorMap tm;
+  memcpy(&tm, tmap_qkv, sizeof(tm));
+  alignas(128) unsigned char part_map[128];
+  ICD_TRY(make_tmap_bf16_2d(part_map, part, (uint64_t)p.QT * B * p.S_pad, (uint64_t)H, (uint32_t)kTile, HD, true));
+  CUtensorMap tc;
+  memcpy(&tc, part_map, sizeof(tc));
+  ICD_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int grid = std::min(p.tiles * kHeads, kSMs);
+  ICD_CUDA(launch_chained(attention_tc_kernel, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, st, 1, tm, tc, p));
+  count_launch();
+  ICD_CUDA(launch_chained(attention_combine_kernel, dim3(B * S), dim3(96), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(part),
+                          reinterpret_cast<const float2*>(stats), B, S, p.S_pad, p.QT, reinterpret_cast<__nv_bfloat16*>(ctx)));
   count_launch();
   return ICD_OK;
 }

@@ -107,109 +107,6 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, int M, const float* __res
   ln_store(x, gamma, beta, eps, out + (size_t)tok * H, lane);
 }
 
-// ---------------------------------------------------------------- attention for 128 < S <= 512
-// The tensor-core kernel (attention_tc.cu) holds one whole sequence in a 128-row tile; longer sequences -- only the
-// token-classification path sends them (the reference's NER pipeline reads up to 512 tokens in one pass,
-// services/medical_ner_service.py:177-229) -- take this kernel: one CTA per (sequence, head, 128-query tile), the
-// K and V rows of the head staged once in shared memory as bf16 (<= 128 KiB), thread == query row, online softmax
-// over the keys j < len in chunks of 4, fp32 accumulation.  CUDA cores: 2 * len * 64 FMAs per query row; at the
-// handful of long texts a request carries this is microseconds, and the layer's GEMMs stay on the tensor cores.
-constexpr int HD = 64;
-constexpr int kLongMaxS = 512;
-__global__ void __launch_bounds__(128)
-attention_long_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
-                      __nv_bfloat16* __restrict__ ctx) {
-  ptx::griddep_launch();
-  ptx::griddep_wait();
-  extern __shared__ __align__(16) unsigned char sm_raw[];
-  uint4* Ks = reinterpret_cast<uint4*>(sm_raw);   // [len][8] uint4 = [len][64] bf16
-  const int b = blockIdx.x, h = blockIdx.y;
-  const int len = min(lens[b], S);
-  uint4* Vs = Ks + (size_t)len * (HD / 8);
-  const size_t row0 = (size_t)b * S;
-  for (int i = threadIdx.x; i < len * (HD / 8); i += blockDim.x) {
-    const int j = i / (HD / 8), c = i % (HD / 8);
-    const __nv_bfloat16* base = qkv + (row0 + j) * (3 * H) + h * HD + c * 8;
-    Ks[i] = *reinterpret_cast<const uint4*>(base + H);
-    Vs[i] = *reinterpret_cast<const uint4*>(base + 2 * H);
-  }
-  __syncthreads();
-  const int t = blockIdx.z * 128 + threadIdx.x;
-  if (t >= S) return;
-  __nv_bfloat16* orow = ctx + (row0 + t) * H + h * HD;
-  if (t >= len) {  // padded query rows are never read downstream (masked keys, masked pooling)
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) *reinterpret_cast<uint4*>(orow + c * 8) = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  float q[HD];
-  {
-    const __nv_bfloat16* qb = qkv + (row0 + t) * (3 * H) + h * HD;
-    const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) and log2(e): the softmax runs in base 2
-#pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      const uint4 v = *reinterpret_cast<const uint4*>(qb + c * 8);
-      q[c * 8 + 0] = bf16lo_to_f32(v.x) * sc; q[c * 8 + 1] = bf16hi_to_f32(v.x) * sc;
-      q[c * 8 + 2] = bf16lo_to_f32(v.y) * sc; q[c * 8 + 3] = bf16hi_to_f32(v.y) * sc;
-      q[c * 8 + 4] = bf16lo_to_f32(v.z) * sc; q[c * 8 + 5] = bf16hi_to_f32(v.z) * sc;
-      q[c * 8 + 6] = bf16lo_to_f32(v.w) * sc; q[c * 8 + 7] = bf16hi_to_f32(v.w) * sc;
-    }
-  }
-  float acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int j0 = 0; j0 < len; j0 += 4) {
-    float s[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = min(j0 + u, len - 1);  // the tail repeats the last key; its weight is zeroed below
-      const uint4* kr = Ks + (size_t)j * (HD / 8);
-      float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        const uint4 k = kr[c];
-        a0 = fmaf(q[c * 8 + 0], bf16lo_to_f32(k.x), a0); a1 = fmaf(q[c * 8 + 1], bf16hi_to_f32(k.x), a1);
-        a0 = fmaf(q[c * 8 + 2], bf16lo_to_f32(k.y), a0); a1 = fmaf(q[c * 8 + 3], bf16hi_to_f32(k.y), a1);
-        a0 = fmaf(q[c * 8 + 4], bf16lo_to_f32(k.z), a0); a1 = fmaf(q[c * 8 + 5], bf16hi_to_f32(k.z), a1);
-        a0 = fmaf(q[c * 8 + 6], bf16lo_to_f32(k.w), a0); a1 = fmaf(q[c * 8 + 7], bf16hi_to_f32(k.w), a1);
-      }
-      s[u] = (j0 + u < len) ? a0 + a1 : -INFINITY;
-    }
-    const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
-    const float corr = exp2f(m - mn);  // 0 for the first chunk (m = -inf)
-    float pw[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) pw[u] = exp2f(s[u] - mn);  // exp2(-inf) = 0 for the masked tail
-    l = fmaf(l, corr, (pw[0] + pw[1]) + (pw[2] + pw[3]));
-    m = mn;
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] *= corr;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint4* vr = Vs + (size_t)min(j0 + u, len - 1) * (HD / 8);
-#pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        const uint4 v = vr[c];
-        acc[c * 8 + 0] = fmaf(pw[u], bf16lo_to_f32(v.x), acc[c * 8 + 0]); acc[c * 8 + 1] = fmaf(pw[u], bf16hi_to_f32(v.x), acc[c * 8 + 1]);
-        acc[c * 8 + 2] = fmaf(pw[u], bf16lo_to_f32(v.y), acc[c * 8 + 2]); acc[c * 8 + 3] = fmaf(pw[u], bf16hi_to_f32(v.y), acc[c * 8 + 3]);
-        acc[c * 8 + 4] = fmaf(pw[u], bf16lo_to_f32(v.z), acc[c * 8 + 4]); acc[c * 8 + 5] = fmaf(pw[u], bf16hi_to_f32(v.z), acc[c * 8 + 5]);
-        acc[c * 8 + 6] = fmaf(pw[u], bf16lo_to_f32(v.w), acc[c * 8 + 6]); acc[c * 8 + 7] = fmaf(pw[u], bf16hi_to_f32(v.w), acc[c * 8 + 7]);
-      }
-    }
-  }
-  const float inv = 1.0f / l;
-#pragma unroll
-  for (int c = 0; c < HD / 8; ++c) {
-    uint4 o;
-    o.x = pack2(acc[c * 8 + 0] * inv, acc[c * 8 + 1] * inv);
-    o.y = pack2(acc[c * 8 + 2] * inv, acc[c * 8 + 3] * inv);
-    o.z = pack2(acc[c * 8 + 4] * inv, acc[c * 8 + 5] * inv);
-    o.w = pack2(acc[c * 8 + 6] * inv, acc[c * 8 + 7] * inv);
-    *reinterpret_cast<uint4*>(orow + c * 8) = o;
-  }
-}
-
 // ---------------------------------------------------------------- masked mean + L2 normalise
 // sentence-transformers Pooling(mean) + F.normalize: sum(h*mask)/clamp(sum(mask),1e-9), then
 // x / max(||x||, 1e-12).  One CTA (256 threads, 3 columns each) per sequence.
@@ -304,23 +201,6 @@ int launch_layernorm(const void* x, int M, const float* gamma, const float* beta
                      cudaStream_t st) {
   ICD_CUDA(launch_chained(layernorm_kernel, dim3((M + 7) / 8), dim3(256), 0, st, 1, reinterpret_cast<const __nv_bfloat16*>(x), M, gamma,
                           beta, eps, reinterpret_cast<__nv_bfloat16*>(out)));
-  count_launch();
-  return ICD_OK;
-}
-
-int launch_attention_long(const void* qkv, const int32_t* lens, int B, int S, void* ctx, cudaStream_t st) {
-  if (S < 1 || S > kLongMaxS) {
-    set_error("attention: S=%d outside [1, %d]", S, kLongMaxS);
-    return ICD_E_UNSUPPORTED;
-  }
-  const size_t smem = (size_t)2 * S * HD * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ICD_CUDA(cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kLongMaxS * HD * 2));
-    attr_set = true;
-  }
-  ICD_CUDA(launch_chained(attention_long_kernel, dim3(B, 12, (S + 127) / 128), dim3(128), smem, st, 1,
-                          reinterpret_cast<const __nv_bfloat16*>(qkv), lens, S, reinterpret_cast<__nv_bfloat16*>(ctx)));
   count_launch();
   return ICD_OK;
 }

@@ -77,8 +77,11 @@ int attention_make_map(void* map128, const void* qkv_bf16, int64_t rows);
 // ctx_rows = rows of the ctx buffer (a multiple of 128 >= B*S): the store boxes are clipped against it
 int launch_attention_tc(const void* tmap_qkv, const int32_t* lens, int B, int S, void* ctx_bf16, int64_t ctx_rows,
                         cudaStream_t st);
-// encoder_kernels.cu: the same for 128 < S <= 512 (token-classification path), K / V of a head in shared memory
-int launch_attention_long(const void* qkv_bf16, const int32_t* lens, int B, int S, void* ctx_bf16, cudaStream_t st);
+// the same for 128 < S <= 512 (token-classification path) on the same tensor-core kernel in split-KV mode: one item per
+// (sequence, head, query tile, key tile), partial outputs + row statistics into scratch, then a combine kernel
+size_t attention_long_scratch_bytes(int B, int S, size_t* stats_bytes);
+int launch_attention_tc_long(const void* tmap_qkv, const int32_t* lens, int B, int S, void* part_scratch, void* stats_scratch,
+                             void* ctx_bf16, cudaStream_t st);
 // masked mean over tokens + L2 normalise -> [B,768] (fp32 or bf16)
 int launch_pool_normalise(const void* h_bf16, const int32_t* lens, int B, int S, void* out, int out_dtype,
                           cudaStream_t st);

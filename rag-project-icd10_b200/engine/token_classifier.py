@@ -9,8 +9,8 @@ the "simple" grouping of adjacent tokens stay on the host, as they do inside the
 (third party, transformers TokenClassificationPipeline: postprocess / gather_pre_entities / aggregate /
 group_entities; restated here, checked against the pipeline itself in tests/test_ner_*.py).
 
-Long texts.  The encoder takes sequences of up to 512 tokens (S <= 128 on the tensor-core attention kernel, longer ones
-on the shared-memory kernel of csrc/encoder_kernels.cu), so a model with a 512-token position table reads a text in ONE
+Long texts.  The encoder takes sequences of up to 512 tokens (S <= 128 is one tile of the tensor-core attention kernel,
+longer ones run it split over 128-key tiles with a combine pass, csrc/attention_tc.cu), so a model with a 512-token position table reads a text in ONE
 pass truncated at 512 tokens, exactly like the reference pipeline.  When the window is shorter than the horizon (an
 encoder built with a smaller max_seq_length), a text that does not fit is cut into overlapping windows (the
 tokenizer's own overflow mechanism, `stride` tokens of overlap) that go through the GPU as one batch, and the windows'
