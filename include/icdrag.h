@@ -77,7 +77,7 @@ int icd_device_count(void);
 /* process-wide tuning knobs of the tensor-core scan (tests and profiling; defaults are right for
  * production): "scan_sample" (stride of the sampling pre-pass, 0 = off, -1 = by table size),
  * "scan_drift" (tiles a CTA may run ahead of its row group, 0 = off), "scan_tmax" (query tiles per
- * row stream per launch, default 16), "scan_bn" (64 | 128 rows per MMA tile), "scan_kbs" /
+ * row stream per launch, default 16), "scan_kbs" /
  * "scan_kbs_pair" (K blocks per pipeline stage for single CTAs / CTA pairs, upper bounds: default 3 / 6),
  * "scan_pair" (CTA pairs: -1 auto, 0 off), "scan_qsplit" (last third of the query tile's K in shared
  * memory so that two accumulator buffers fit: -1 auto, 0 off), "scan_qtmem" (K blocks kept in TMEM when

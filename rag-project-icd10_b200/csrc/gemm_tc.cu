@@ -543,7 +543,10 @@ int launch_gemm_tc(const GemmArgs& a, cudaStream_t st) {
   p.N = a.N;
   p.K = a.K;
   p.epi = a.epi;
-  return pair_mode() == 2 ? launch_nc<2>(ta, tb, tout, tres, p, st) : launch_nc<1>(ta, tb, tout, tres, p, st);
+#ifdef ICD_PROFILING
+  if (pair_mode() != 2) return launch_nc<1>(ta, tb, tout, tres, p, st);   // single-CTA tiles: A/B timing only
+#endif
+  return launch_nc<2>(ta, tb, tout, tres, p, st);
 }
 
 int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K) {

@@ -637,7 +637,7 @@ static int env_int(const char* name, int dflt) {
 struct Tunables {
   int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, pre_slots, gen;
   Tunables() {
-    bn = env_int("ICD_SCAN_BN", 128) == 64 ? 64 : 128;
+    bn = 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
     tmax = std::min(32, std::max(1, env_int("ICD_SCAN_TMAX", 16)));
     kbs = std::min(6, std::max(1, env_int("ICD_SCAN_KBS", 3)));            // K blocks per stage, single CTAs
@@ -662,8 +662,7 @@ static int scan_tmax() { return tun().tmax; }
 
 int tensor_scan_tune(const char* key, int value) {
   Tunables& t = tun();
-  if (!strcmp(key, "scan_bn")) t.bn = value == 64 ? 64 : 128;
-  else if (!strcmp(key, "scan_drift")) t.drift = std::max(0, value);
+  if (!strcmp(key, "scan_drift")) t.drift = std::max(0, value);
   else if (!strcmp(key, "scan_tmax")) t.tmax = std::min(32, std::max(1, value));
   else if (!strcmp(key, "scan_kbs")) t.kbs = std::min(6, std::max(1, value));
   else if (!strcmp(key, "scan_kbs_pair")) t.kbs_pair = std::min(6, std::max(1, value));
@@ -901,7 +900,8 @@ int launch_tensor_scan(const TensorScanArgs& a, const void* map128, cudaStream_t
     set_error("tensor scan: unsupported dim=%d k=%d", a.dim, a.k);
     return ICD_E_UNSUPPORTED;
   }
-  return scan_bn() == 64 ? launch_tensor_scan_bn<64>(a, map128, st) : launch_tensor_scan_bn<128>(a, map128, st);
+  // BN = 128 only: with the query tile in tensor memory an N = 64 MMA runs the pipe at half rate (r01: 38 % tensor-active)
+  return launch_tensor_scan_bn<128>(a, map128, st);
 }
 
 }  // namespace icd
