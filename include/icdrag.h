@@ -82,7 +82,8 @@ int icd_device_count(void);
  * "scan_pair" (CTA pairs: -1 auto, 0 off), "scan_qsplit" (last third of the query tile's K in shared
  * memory so that two accumulator buffers fit: -1 auto, 0 off), "scan_qtmem" (K blocks kept in TMEM when
  * split, 0 = all that fit), "scan_generic" (1 = the run-time-shaped MMA issue loop instead of the unrolled one), "scan_pre_slots"
- * (0 = the list-based sampling pre-pass instead of the slot-maxima one), "enc_pdl" (0 = plain stream order between the
+ * (0 = the list-based sampling pre-pass instead of the slot-maxima one), "scan_small_pre" (0 = no pre-pass on tables
+ * below 512 k rows), "enc_pdl" (0 = plain stream order between the
  * encoder's kernels instead of programmatic dependent launch).
  * Results never depend on them.  Production builds read NO environment variables on the compute path; profiling
  * builds (-DICD_PROFILING) additionally honour ICD_SCAN_*, ICD_GEMM_PAIR, ICD_ENC_FUSED_LN, ICD_ATTN_DBG. */

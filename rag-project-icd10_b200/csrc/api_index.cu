@@ -161,10 +161,10 @@ int index_search_device(icd_index* x, int B, int k, int weight_mode, int path, i
       if (sample > 1) {
         // sampling pre-pass over every `sample`-th row tile: a proven lower bound of the final kc-th best score per
         // query, so the main scan admits only rows that reach it (about kc * sample rows per query instead of every row
-        // of each list's warm-up).  kc <= 32: slot maxima, no lists (scan_tc.cu, PRE); larger kc: exact top-kc of the
-        // sample through the list path and the merge.
+        // of each list's warm-up).  Slot maxima, no lists (scan_tc.cu, PRE; every kc <= 128); the list path (exact top-kc
+        // of the sample, then the merge) remains behind icd_tune("scan_pre_slots", 0) for A/B.
         a.tile_stride = sample;
-        if (kc <= tensor_scan_pre_slots() && tensor_scan_pre_mode() != 0) {
+        if (kc <= tensor_scan_pre_capacity() && tensor_scan_pre_mode() != 0) {
           a.pre_slots = 1;
           ICD_TRY(launch_tensor_scan(a, x->tmap, st));
           a.pre_slots = 0;

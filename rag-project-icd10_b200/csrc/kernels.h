@@ -46,6 +46,7 @@ struct TensorScanArgs {
                       // running maxima instead of sorted lists, part_id is untouched; feed launch_bound_from_slots
 };
 int tensor_scan_pre_slots();
+int tensor_scan_pre_capacity();   // largest kc the slot-maxima bound serves (slots x the row-group classes it keeps apart)
 int tensor_scan_pre_mode();   // 1 = slot-maxima pre-pass (default), 0 = list-based pre-pass (icd_tune "scan_pre_slots")
 // stride of the sampling pre-pass for a table of n_rows when the scan keeps kc candidates per query (0 = no pre-pass)
 int tensor_scan_sample_stride(int64_t n_rows, int kc);
@@ -72,8 +73,9 @@ struct MergeArgs {
                              // the list holds fewer than k_out rows) -- the admission bound of the main scan
 };
 int launch_merge(const MergeArgs& a, cudaStream_t st);
-// pre-pass bound: per query the kc-th largest of the slot maxima (each slot's maximum taken over the P groups) as an
-// order-preserving key in bound_key_out[b]; slots is tensor_scan_pre_slots() (32), kc <= slots
+// pre-pass bound: per query the kc-th largest of the slot maxima (each slot's maximum taken over the row groups of one
+// class g mod 4) as an order-preserving key in bound_key_out[b]; slots is tensor_scan_pre_slots() (32),
+// kc <= tensor_scan_pre_capacity() (128)
 int launch_bound_from_slots(const float* slot_max /*[B, P, slots]*/, int B, int P, int slots, int kc, int* bound_key_out,
                             cudaStream_t st);
 

@@ -67,7 +67,9 @@ constexpr int kMaxStages = 12;
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kPreSlots = 32;  // running maxima per query in the pre-pass (>= kc of every launch that uses it)
+constexpr int kPreSlots = 32;  // running maxima per (query, row group) in the pre-pass
+constexpr int kPreFolds = 4;   // row groups fold into this many classes (g mod 4): 128 disjoint row sets per query, so the
+                               // slot-maxima bound serves every kc <= 128 (topk_merge.cu, bound_from_slots_kernel)
 
 struct ScanParams {
   const uint8_t* levels;
@@ -98,8 +100,12 @@ struct ScanParams {
 // shared memory, entry j of this thread at [j * BM].  Rows arrive in ascending id order, so a
 // strict '>' admission test plus "insert after equal scores" keeps the id tie-break exact.
 // (An unsorted list with worst-slot tracking was measured slower: 60 % vs 71 % of HBM at B=128.)
-__device__ __noinline__ float list_insert(float* ls, int* li, int kc, float s, int id) {
-  int j = kc - 1;  // precondition: s > ls[(kc-1)*BM]
+// `cnt` = entries filled so far: the walk starts at the first free entry instead of at the end of the list, so a list that
+// a tight pre-pass bound keeps nearly empty (a handful of admitted rows per row group) pays a handful of steps per insert,
+// not kc (r02s: on the 40 474-row table every insert used to shift through all 36 entries, ~1 k cycles for the warp).
+__device__ __noinline__ float list_insert(float* ls, int* li, int kc, int& cnt, float s, int id) {
+  int j = cnt < kc ? cnt : kc - 1;  // precondition when the list is full: s > ls[(kc-1)*BM]
+  cnt = cnt < kc ? cnt + 1 : kc;
   while (j > 0 && ls[(j - 1) * BM] < s) {
     ls[j * BM] = ls[(j - 1) * BM];
     li[j * BM] = li[(j - 1) * BM];
@@ -445,6 +451,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     float thr = live ? -INFINITY : INFINITY;  // k-th best of this CTA's list (strict admission)
     float adm = thr;                          // admission threshold: max(thr, just below the global bound)
     float published = -INFINITY;
+    int cnt = 0;  // filled entries of this thread's list
     int* gb = (p.gbound && live) ? p.gbound + query : nullptr;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     int it = 0;
@@ -499,7 +506,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             const int cc = c32 * 32 + c;
             const float s = __uint_as_float(r[cc]);
             if (s > adm && cc < valid) {
-              thr = list_insert(my_s, my_i, p.kc, s, (int)(row0 + cc));
+              thr = list_insert(my_s, my_i, p.kc, cnt, s, (int)(row0 + cc));
               adm = fmaxf(adm, thr);
             }
           }
@@ -635,7 +642,7 @@ static int env_int(const char* name, int dflt) {
 #endif
 }
 struct Tunables {
-  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, pre_slots, gen;
+  int bn, drift, tmax, kbs, kbs_pair, sample, qsplit, pair, qtmem, generic, tiled, pre_slots, small_pre, gen;
   Tunables() {
     bn = 128;
     drift = std::max(0, env_int("ICD_SCAN_DRIFT", 4));
@@ -648,6 +655,7 @@ struct Tunables {
     qtmem = env_int("ICD_SCAN_QTMEM", 0);      // K blocks of the query tile kept in TMEM when split (0 = all that fit: 8)
     tiled = 0;
     pre_slots = 1;
+    small_pre = 1;   // pre-pass on tables below 512 k rows (icd_tune "scan_small_pre", 0 = round-2 behaviour: none)
     generic = env_int("ICD_SCAN_GENERIC", 0);   // 1 = always the generic (run-time shape) issue loop: A/B only
     gen = 0;
   }
@@ -672,6 +680,7 @@ int tensor_scan_tune(const char* key, int value) {
   else if (!strcmp(key, "scan_qtmem")) t.qtmem = std::max(0, value);
   else if (!strcmp(key, "scan_generic")) t.generic = value != 0;
   else if (!strcmp(key, "scan_pre_slots")) t.pre_slots = value != 0;
+  else if (!strcmp(key, "scan_small_pre")) t.small_pre = value != 0;
 #ifdef ICD_PROFILING
   else if (!strcmp(key, "scan_tiled")) t.tiled = value != 0;
 #endif
@@ -683,18 +692,23 @@ int tensor_scan_generation() { return tun().gen; }
 
 int tensor_scan_max_partials() { return kSMs; }
 int tensor_scan_pre_slots() { return kPreSlots; }
+int tensor_scan_pre_capacity() { return kPreSlots * kPreFolds; }
 int tensor_scan_pre_mode() { return tun().pre_slots; }
 int tensor_scan_sample_stride(int64_t n_rows, int kc) {
   const int forced = tun().sample;
   if (forced >= 0) return forced <= 1 ? 0 : forced;
-  if (kc > kPreSlots || tun().pre_slots == 0) {
+  if (kc > kPreSlots * kPreFolds || tun().pre_slots == 0) {
     // list-based pre-pass (its warm-up inserts cost as much as they save on small tables): calibrated in round 1
     return n_rows >= (2 << 20) ? 256 : (n_rows >= (1 << 19) ? 64 : 0);
   }
   // slot-maxima pre-pass: its cost is the sampled rows' share of the stream (rows / stride), its gain the main scan's
   // warm-up inserts (~ log of the stride), so the optimum keeps the SAMPLE at about 200 k rows whatever the table size:
   // stride 8 at 1 M rows (0.48 vs 1.02 ms with 256), 64 at 12.5 M, 256 at 100 M (profiles/r02k_prepass_stride_ab.jsonl)
-  if (n_rows < (1 << 19)) return 0;  // below ~0.5 M rows a search is a few tens of microseconds: two more launches do not pay
+  // Small tables (the reference's own 40 474 rows, BASELINE configs[1]): WITHOUT a bound every (query, row group) list
+  // warms up on its own -- kc (1 + ln(rows per group / kc)) divergent inserts per thread, ~2 ms at B = 1024 against
+  // ~0.05 ms of MMA work (r02m) -- so here the pre-pass is worth even half of the table: every second row tile.
+  if (n_rows < (1 << 17)) return tun().small_pre ? 2 : 0;
+  if (n_rows < (1 << 19)) return tun().small_pre ? 4 : 0;
   int stride = 4;
   while (stride < 256 && (double)n_rows / (2.0 * stride) > 141000.0) stride *= 2;  // nearest power of two to rows / 200 k
   return stride;

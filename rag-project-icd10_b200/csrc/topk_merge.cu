@@ -75,25 +75,43 @@ merge_kernel(const float* __restrict__ part_score, const int* __restrict__ part_
   }
 }
 
-// Pre-pass bound (scan_tc.cu, PRE): lane j owns slot j; its value is the maximum of that slot over the P row groups.  Slots
-// partition the sampled rows, so the kc-th largest slot value is reached by >= kc distinct rows: a proven lower bound of the
-// kc-th best score of the table.  One warp per query.
+// Pre-pass bound (scan_tc.cu, PRE).  The pre-pass left one running maximum per (query, row group g, slot j) -- slot =
+// accumulator column mod 32 -- and these P x 32 maxima belong to DISJOINT sets of sampled rows.  Row groups fold into
+// kFolds classes (g mod kFolds), which leaves kFolds x 32 = 128 disjoint sets per query; the kc-th largest of their maxima
+// is reached by >= kc distinct rows: a proven lower bound of the kc-th best score of the table, for every kc <= 128.
+// (Round 2 folded all groups into one class: 32 sets, kc <= 32, and a bound at about the 1.4 kc-th best sampled score; with
+// 128 sets it sits at about the 1.1 kc-th.)  One warp per query: lane j owns slot j of every class, ranks by counting.
+constexpr int kFolds = 4;
 __global__ void __launch_bounds__(kMergeWarps * 32)
 bound_from_slots_kernel(const float* __restrict__ slot_max, int B, int P, int kc, int* __restrict__ bound_key_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kMergeWarps + warp;
   if (b >= B) return;
   const float* base = slot_max + (size_t)b * P * 32;
-  float m = -INFINITY;
-  for (int g = 0; g < P; ++g) m = fmaxf(m, base[(size_t)g * 32 + lane]);
-  // rank of this lane's value among the 32 (descending, ties by lane)
-  int rank = 0;
+  float m[kFolds];
 #pragma unroll
-  for (int o = 0; o < 32; ++o) {
-    const float v = __shfl_sync(0xffffffffu, m, o);
-    rank += (v > m || (v == m && o < lane)) ? 1 : 0;
+  for (int f = 0; f < kFolds; ++f) m[f] = -INFINITY;
+  for (int g0 = 0; g0 < P; g0 += kFolds) {
+#pragma unroll
+    for (int f = 0; f < kFolds; ++f)
+      if (g0 + f < P) m[f] = fmaxf(m[f], base[(size_t)(g0 + f) * 32 + lane]);
   }
-  if (rank == kc - 1) bound_key_out[b] = (m == -INFINITY) ? (int)0x80808080 : float_key(m);
+  // rank of each of this lane's values among the 128 (descending, ties by index f * 32 + lane)
+  int rank[kFolds];
+#pragma unroll
+  for (int f = 0; f < kFolds; ++f) rank[f] = 0;
+  for (int o = 0; o < 32; ++o) {
+#pragma unroll
+    for (int fo = 0; fo < kFolds; ++fo) {
+      const float v = __shfl_sync(0xffffffffu, m[fo], o);
+#pragma unroll
+      for (int f = 0; f < kFolds; ++f)
+        rank[f] += (v > m[f] || (v == m[f] && fo * 32 + o < f * 32 + lane)) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < kFolds; ++f)
+    if (rank[f] == kc - 1) bound_key_out[b] = (m[f] == -INFINITY) ? (int)0x80808080 : float_key(m[f]);
 }
 
 // canonical exact dot: chunk c of the row belongs to lane c%32, chunks ascending, elements
@@ -305,7 +323,7 @@ int launch_merge(const MergeArgs& a, cudaStream_t st) {
 }
 
 int launch_bound_from_slots(const float* slot_max, int B, int P, int slots, int kc, int* bound_key_out, cudaStream_t st) {
-  if (slots != 32 || kc < 1 || kc > 32 || P < 1) {
+  if (slots != 32 || kc < 1 || kc > 32 * kFolds || P < 1) {
     set_error("bound_from_slots: slots=%d kc=%d P=%d", slots, kc, P);
     return ICD_E_ARG;
   }

@@ -222,8 +222,8 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
     """The sampling pre-pass (admission bound from every s-th row tile), the drift limiter and the
     launch shaping and the placement of the query tile (all of K in tensor memory, or its last third in shared
     memory so that two accumulator buffers fit) are performance devices: with any setting the tensor scan returns the oracle's
-    top-k.  Forced on here at sizes the oracle finishes in seconds (by default the pre-pass
-    only runs on tables of >= 2 M rows)."""
+    top-k.  Strides forced here at sizes the oracle finishes in seconds (by default: every 2nd row tile below 128 k
+    rows, every 4th below 512 k, then whatever keeps the sample near 200 k rows)."""
     n, B, k, dim = 60000, 300, 10, 768
     corpus = _corpus(n, dim, seed=21)
     # duplicate rows make exact score ties across row tiles: the bound must admit equal scores
@@ -256,18 +256,21 @@ def test_tensor_scan_knobs_keep_results_exact(pkg, native, knobs, weight_mode):
     idx.close()
 
 
-@pytest.mark.parametrize("k", [10, 26, 27, 60])
-def test_pre_pass_bound_is_valid_for_every_k(pkg, native, k):
-    """The pre-pass bound must never exceed the true kc-th best score: slot maxima for kc <= 32 (k <= 26), the list-based
-    pre-pass beyond; a tiny table with a forced stride makes slots sparse (some stay empty)."""
+@pytest.mark.parametrize("keep_f32", [False, True])
+@pytest.mark.parametrize("k", [10, 26, 27, 60, 128])
+def test_pre_pass_bound_is_valid_for_every_k(pkg, native, k, keep_f32):
+    """The pre-pass bound must never exceed the true kc-th best score.  Slot maxima: 32 slots x 4 classes of row groups =
+    128 disjoint row sets per query, the kc-th largest of their maxima (kc = k + 6, or 2 k + 16 with the fp32 master
+    rows: up to 128); a small table with a large forced stride makes the sets sparse (most stay empty: the bound
+    falls back to -inf and nothing is pruned)."""
     n, B, dim = 30000, 130, 768
     corpus = _corpus(n, dim, seed=41)
     levels = _levels(n, seed=42)
     q = _corpus(B, dim, seed=43)
     q[:16] = corpus[777:793]
-    idx = _index(pkg, corpus, levels)
+    idx = _index(pkg, corpus, levels, keep_f32=keep_f32)
     try:
-        for stride in (2, 64):
+        for stride in (2, 7, 64):
             native.tune(scan_sample=stride)
             score, raw, ids = idx.search(q, k, weight_mode=native.WEIGHT_NONE, path=native.PATH_TENSOR)
             ref_s, ref_i = osearch.exact_topk(corpus, q, k)
@@ -315,6 +318,41 @@ def test_cta_pair_scan_equals_single_cta_scan(pkg, native, knobs):
         np.testing.assert_allclose(s3[b], r3[b] * w[i3[b]], rtol=1e-6)
         assert np.all(s3[b][:-1] >= s3[b][1:])
     idx.close()
+
+
+@pytest.mark.parametrize("keep_f32", [False, True])
+@pytest.mark.parametrize("n,B,k", [(1024, 5, 10), (1500, 64, 1), (4097, 300, 10), (40474, 130, 100), (40474, 1030, 10),
+                                    (131072, 257, 10), (200000, 40, 27)])
+def test_small_table_pre_pass_is_a_performance_device(pkg, native, n, B, k, keep_f32):
+    """Tables below 512 k rows (the reference's own 40 474) run the slot-maxima pre-pass over every 2nd (from 128 k rows:
+    every 4th) row tile so that the main scan's lists do not warm up row group by row group.  Same results bit for bit
+    with it and without it (icd_tune scan_small_pre = 0, the round-2 behaviour), and both equal the oracle's top-k."""
+    dim = 768
+    corpus = _corpus(n, dim, seed=n + k)
+    corpus[n // 3:n // 3 + 8] = corpus[n - 8:]                       # exact ties between a sampled and an unsampled tile
+    levels = _levels(n, seed=n + 1)
+    q = _corpus(B, dim, seed=B + k)
+    q[:4] = corpus[n - 4:]
+    idx = _index(pkg, corpus, levels, keep_f32=keep_f32)
+    try:
+        got = {}
+        for pre in (1, 0):
+            native.tune(scan_small_pre=pre)
+            for wm in (native.WEIGHT_NONE, native.WEIGHT_RERANK, native.WEIGHT_PRE):
+                got[pre, wm] = idx.search(q, k, weight_mode=wm, path=native.PATH_TENSOR)
+    finally:
+        native.tune(scan_small_pre=1)
+    idx.close()
+    for wm in (native.WEIGHT_NONE, native.WEIGHT_RERANK, native.WEIGHT_PRE):
+        for a, b in zip(got[1, wm], got[0, wm]):
+            assert np.array_equal(a, b), (wm, n, B, k)
+    score, raw, ids = got[1, native.WEIGHT_NONE]
+    ref_s, ref_i = osearch.exact_topk(corpus, q, k)
+    swaps = check_topk(ids, raw, ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    assert swaps <= max(1, B * k // 50)
+    for b in range(4):                                                # the planted duplicates, lower id first
+        if k >= 2:
+            assert ids[b, 0] == n // 3 + 4 + b and ids[b, 1] == n - 4 + b, (b, ids[b, :3])
 
 
 def test_config1_10k_queries_against_the_icd_sized_corpus(pkg, native):
