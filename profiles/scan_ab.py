@@ -15,7 +15,7 @@ warm = int(os.environ.get("WARM", 2))
 variants = [v for v in os.environ.get("VARIANTS", "scan_pair=-1;scan_pair=0").split(";") if v]
 DEFAULTS = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_kbs_pair=6, scan_qsplit=-1, scan_pair=-1, scan_qtmem=0,
                 scan_generic=0, scan_pre_slots=1)
-if os.environ.get("PROF_LIB"):
+if os.environ.get("PROF_LIB") and os.environ.get("PROF_TILED"):   # profiling builds only (make PROFILING=1)
     DEFAULTS["scan_tiled"] = 0
 dev = torch.device("cuda", 0)
 table, levels = bench.make_corpus(torch, rows, dev, 1234)

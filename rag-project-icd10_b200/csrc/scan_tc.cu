@@ -100,20 +100,32 @@ struct ScanParams {
 // shared memory, entry j of this thread at [j * BM].  Rows arrive in ascending id order, so a
 // strict '>' admission test plus "insert after equal scores" keeps the id tie-break exact.
 // (An unsorted list with worst-slot tracking was measured slower: 60 % vs 71 % of HBM at B=128.)
+// Admitted scores wait in a small per-thread FIFO (local memory: dynamically indexed, L1-resident) and reach the sorted
+// list here, all lanes of the warp together.  Every queued score is tested again against the list's current k-th best.
 // `cnt` = entries filled so far: the walk starts at the first free entry instead of at the end of the list, so a list that
-// a tight pre-pass bound keeps nearly empty (a handful of admitted rows per row group) pays a handful of steps per insert,
-// not kc (r02s: on the 40 474-row table every insert used to shift through all 36 entries, ~1 k cycles for the warp).
-__device__ __noinline__ float list_insert(float* ls, int* li, int kc, int& cnt, float s, int id) {
-  int j = cnt < kc ? cnt : kc - 1;  // precondition when the list is full: s > ls[(kc-1)*BM]
-  cnt = cnt < kc ? cnt + 1 : kc;
-  while (j > 0 && ls[(j - 1) * BM] < s) {
-    ls[j * BM] = ls[(j - 1) * BM];
-    li[j * BM] = li[(j - 1) * BM];
-    --j;
+// a tight pre-pass bound keeps nearly empty pays a handful of steps per insert, not kc.
+// Returns (k-th best, filled entries).  One call site per accumulator tile plus the rare "queue nearly full" sites, so
+// the unrolled 128-column epilogue stays small (inlined per column, the insert path made the kernel 12.8 k instructions
+// and twice as slow as the instruction cache missed: r02u).
+constexpr int kQueue = 8;
+__device__ __noinline__ uint2 drain_queue(float* ls, int* li, int kc, int cnt, float thr, const float* qs, const int* qi, int qn) {
+  for (int e = 0; e < qn; ++e) {
+    const float s = qs[e];
+    if (s > thr) {
+      const int id = qi[e];
+      int j = cnt < kc ? cnt : kc - 1;  // first free entry, or the last one of a full list (s > ls[(kc-1)*BM] then)
+      cnt = cnt < kc ? cnt + 1 : kc;
+      while (j > 0 && ls[(j - 1) * BM] < s) {
+        ls[j * BM] = ls[(j - 1) * BM];
+        li[j * BM] = li[(j - 1) * BM];
+        --j;
+      }
+      ls[j * BM] = s;
+      li[j * BM] = id;
+      thr = ls[(kc - 1) * BM];
+    }
   }
-  ls[j * BM] = s;
-  li[j * BM] = id;
-  return ls[(kc - 1) * BM];
+  return make_uint2(__float_as_uint(thr), (uint32_t)cnt);
 }
 
 // BN = table rows per accumulator tile (MMA N); NC = CTAs per MMA (2 = CTA pair, cta_group::2).
@@ -447,11 +459,30 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
   } else {
     // ===================== epilogue: fused top-k =====================
+    // Admitted scores do not go into the sorted list one by one: a lane parks them in its FIFO and the warp empties all
+    // queues together once per tile (drain_queue).  On large tables admissions are rare either way; on small ones
+    // (40 474 rows: ~80 admitted rows per query over 317 tiles, i.e. ~8 per warp and tile, each in a different lane and
+    // column) every admission used to cost the whole warp one divergent insert call -- r02t (ncu, B = 8192): 1 360
+    // instructions per warp and tile, 480 of them inside list_insert, the MMA thread waiting on the accumulator
+    // barrier 106 polls per tile.  Queued, the same admissions cost one convergent drain per tile.
+    // Rows still reach a lane's list in ascending id order (columns are tested in ascending order, the queue is
+    // FIFO), which the strict '>' admission relies on for the id tie-break.
     const bool live = query < p.B;
     float thr = live ? -INFINITY : INFINITY;  // k-th best of this CTA's list (strict admission)
     float adm = thr;                          // admission threshold: max(thr, just below the global bound)
     float published = -INFINITY;
-    int cnt = 0;  // filled entries of this thread's list
+    int cnt = 0;                              // filled entries of this thread's list
+    float qs[kQueue];                         // parked candidates
+    int qi[kQueue];
+    int qn = 0;
+    const int kc = p.kc;
+    auto drain = [&]() {
+      const uint2 tc = drain_queue(my_s, my_i, kc, cnt, thr, qs, qi, qn);
+      thr = __uint_as_float(tc.x);
+      cnt = (int)tc.y;
+      qn = 0;
+      adm = fmaxf(adm, thr);
+    };
     int* gb = (p.gbound && live) ? p.gbound + query : nullptr;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     int it = 0;
@@ -494,24 +525,35 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             r[cc] = __float_as_uint(__uint_as_float(r[cc]) * level_weight_f(lv));
           }
         }
+        // maxima of the eight groups of four CONSECUTIVE columns: a group is looked into only if its maximum passes
         float m8[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) m8[c] = __uint_as_float(r[c32 * 32 + c]);
-#pragma unroll
-        for (int c = 8; c < 32; ++c) m8[c & 7] = fmaxf(m8[c & 7], __uint_as_float(r[c32 * 32 + c]));
+        for (int j = 0; j < 8; ++j) {
+          const int c0 = c32 * 32 + 4 * j;
+          m8[j] = fmaxf(fmaxf(__uint_as_float(r[c0]), __uint_as_float(r[c0 + 1])),
+                        fmaxf(__uint_as_float(r[c0 + 2]), __uint_as_float(r[c0 + 3])));
+        }
         const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
         if (m > adm) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int cc = c32 * 32 + c;
-            const float s = __uint_as_float(r[cc]);
-            if (s > adm && cc < valid) {
-              thr = list_insert(my_s, my_i, p.kc, cnt, s, (int)(row0 + cc));
-              adm = fmaxf(adm, thr);
+          for (int j = 0; j < 8; ++j) {
+            if (m8[j] > adm) {
+              if (qn > kQueue - 4) drain();  // room for the four columns of this group
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int cc = c32 * 32 + 4 * j + e;
+                const float sv = __uint_as_float(r[cc]);
+                if (sv > adm && cc < valid) {
+                  qs[qn] = sv;
+                  qi[qn] = (int)(row0 + cc);
+                  ++qn;
+                }
+              }
             }
           }
         }
       }
+      if (__any_sync(0xffffffffu, qn > 0)) drain();
       if (gb && thr > published) {
         atomicMax(gb, float_key(thr));
         published = thr;
@@ -830,6 +872,7 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
   // CTAs at B = 128 peak at 3).  Largest divisor of nkb <= the knob that still leaves >= 3 stages beside the Q tail;
   // if none does, the split goes first, then the stage shrinks.
   const int kbs_want = std::min(pair ? tun().kbs_pair : tun().kbs, nkb);
+  const int kc_smem = a.pre_slots ? 0 : a.k;  // the slot-maxima pre-pass keeps no lists: its stages get that room
   int kbs = 0, nkb_tmem = nkb, q_tail_tiles = 0, nst = 0;
   for (int pass = 0; pass < 2 && kbs == 0; ++pass) {
     const bool split = pass == 0 && want_split;
@@ -842,8 +885,8 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     for (int c = kbs_want; c >= 1 && kbs == 0; --c) {
       if (nkb % c) continue;
       int n = kMaxStages;
-      while (n > 2 && smem_bytes(BN / NC, n, c, a.k, nkb - tmem_kb) > (size_t)kSmemLimit) --n;
-      if (smem_bytes(BN / NC, n, c, a.k, nkb - tmem_kb) > (size_t)kSmemLimit) continue;
+      while (n > 2 && smem_bytes(BN / NC, n, c, kc_smem, nkb - tmem_kb) > (size_t)kSmemLimit) --n;
+      if (smem_bytes(BN / NC, n, c, kc_smem, nkb - tmem_kb) > (size_t)kSmemLimit) continue;
       if (split && n < 3) continue;
       kbs = c, nst = n, nkb_tmem = tmem_kb, q_tail_tiles = nkb - tmem_kb;
     }
@@ -852,7 +895,9 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     set_error("tensor scan: k=%d does not fit shared memory", a.k);
     return ICD_E_UNSUPPORTED;
   }
-  const size_t smem = smem_bytes(BN / NC, nst, kbs, a.k, q_tail_tiles);
+  const size_t smem = smem_bytes(BN / NC, nst, kbs, kc_smem, q_tail_tiles);
+  // a table that stays in L2 needs no drift limiter (its polls only cost latency there)
+  const bool l2_table = (size_t)a.n_rows * a.dim * 2 <= ((size_t)64 << 20);
   // the stage shape is chosen per launch, so the 3-D view {64 elements, rows, K blocks} of the table is encoded here
   // (a host-side call of a few microseconds); each CTA of a pair loads half of a row tile
   (void)map128;
@@ -880,7 +925,7 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.dim = a.dim;
     p.nkb = a.dim / BK;
     p.B = a.B;
-    p.kc = a.k;
+    p.kc = kc_smem;
     p.weight_pre = a.weight_pre;
     p.G = G;
     p.T = std::min(T_launch, T_total - qt0);
@@ -892,7 +937,7 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     p.nacc = (kTmemCols - p.acc_col0) / BN >= 2 ? 2 : 1;
     p.tstride = tstride;
     p.drift = scan_drift();
-    p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64) ? a.progress + (size_t)launch * kSMs : nullptr;
+    p.progress = (a.progress && p.drift > 0 && p.T > 1 && launch < 64 && !l2_table) ? a.progress + (size_t)launch * kSMs : nullptr;
 #ifdef ICD_PROFILING
     p.tiled = (tun().tiled && BN == 128) ? 1 : 0;
 #endif
@@ -900,6 +945,7 @@ static int launch_tensor_scan_bn(const TensorScanArgs& a, const void* map128, cu
     const bool pre = a.pre_slots != 0;
     const bool spec = BN == 128 && a.dim == 768 && nkb_tmem == 8 && tun().generic == 0;
     if (pair && spec && kbs == 6) ICD_TRY((launch_one<BN, 2, 6, 8>(tmap, p, G * p.T, smem, st, pre)));
+    else if (pair && spec && kbs == 4) ICD_TRY((launch_one<BN, 2, 4, 8>(tmap, p, G * p.T, smem, st, pre)));  // kc = 36 lists
     else if (pair && spec && kbs == 3) ICD_TRY((launch_one<BN, 2, 3, 8>(tmap, p, G * p.T, smem, st, pre)));
     else if (pair) ICD_TRY((launch_one<BN, 2, 0, 0>(tmap, p, G * p.T, smem, st, pre)));
     else if (spec && kbs == 3) ICD_TRY((launch_one<BN, 1, 3, 8>(tmap, p, G * p.T, smem, st, pre)));

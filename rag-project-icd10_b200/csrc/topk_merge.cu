@@ -80,38 +80,36 @@ merge_kernel(const float* __restrict__ part_score, const int* __restrict__ part_
 // kFolds classes (g mod kFolds), which leaves kFolds x 32 = 128 disjoint sets per query; the kc-th largest of their maxima
 // is reached by >= kc distinct rows: a proven lower bound of the kc-th best score of the table, for every kc <= 128.
 // (Round 2 folded all groups into one class: 32 sets, kc <= 32, and a bound at about the 1.4 kc-th best sampled score; with
-// 128 sets it sits at about the 1.1 kc-th.)  One warp per query: lane j owns slot j of every class, ranks by counting.
+// 128 sets it sits at about the 1.1 kc-th.)
 constexpr int kFolds = 4;
-__global__ void __launch_bounds__(kMergeWarps * 32)
+// One block of kFolds warps per query: warp f folds the row groups of class f (lane = slot; 8 independent loads in
+// flight, the chain of P dependent L2 round trips was ~30 us at small batches), the 128 maxima meet in shared memory and
+// every thread ranks its own value by counting (descending, ties by index).
+__global__ void __launch_bounds__(kFolds * 32)
 bound_from_slots_kernel(const float* __restrict__ slot_max, int B, int P, int kc, int* __restrict__ bound_key_out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kMergeWarps + warp;
-  if (b >= B) return;
-  const float* base = slot_max + (size_t)b * P * 32;
-  float m[kFolds];
+  __shared__ float vals[kFolds * 32];
+  const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const float* base = slot_max + (size_t)b * P * 32 + lane;
+  float m = -INFINITY;
+  int g = f;
+  for (; g + 7 * kFolds < P; g += 8 * kFolds) {
+    float v[8];
 #pragma unroll
-  for (int f = 0; f < kFolds; ++f) m[f] = -INFINITY;
-  for (int g0 = 0; g0 < P; g0 += kFolds) {
+    for (int u = 0; u < 8; ++u) v[u] = base[(size_t)(g + u * kFolds) * 32];
 #pragma unroll
-    for (int f = 0; f < kFolds; ++f)
-      if (g0 + f < P) m[f] = fmaxf(m[f], base[(size_t)(g0 + f) * 32 + lane]);
+    for (int u = 0; u < 8; ++u) m = fmaxf(m, v[u]);
   }
-  // rank of each of this lane's values among the 128 (descending, ties by index f * 32 + lane)
-  int rank[kFolds];
-#pragma unroll
-  for (int f = 0; f < kFolds; ++f) rank[f] = 0;
-  for (int o = 0; o < 32; ++o) {
-#pragma unroll
-    for (int fo = 0; fo < kFolds; ++fo) {
-      const float v = __shfl_sync(0xffffffffu, m[fo], o);
-#pragma unroll
-      for (int f = 0; f < kFolds; ++f)
-        rank[f] += (v > m[f] || (v == m[f] && fo * 32 + o < f * 32 + lane)) ? 1 : 0;
-    }
+  for (; g < P; g += kFolds) m = fmaxf(m, base[(size_t)g * 32]);
+  vals[threadIdx.x] = m;
+  __syncthreads();
+  int rank = 0;
+#pragma unroll 8
+  for (int o = 0; o < kFolds * 32; ++o) {
+    const float v = vals[o];
+    rank += (v > m || (v == m && o < (int)threadIdx.x)) ? 1 : 0;
   }
-#pragma unroll
-  for (int f = 0; f < kFolds; ++f)
-    if (rank[f] == kc - 1) bound_key_out[b] = (m[f] == -INFINITY) ? (int)0x80808080 : float_key(m[f]);
+  if (rank == kc - 1) bound_key_out[b] = (m == -INFINITY) ? (int)0x80808080 : float_key(m);
 }
 
 // canonical exact dot: chunk c of the row belongs to lane c%32, chunks ascending, elements
@@ -327,8 +325,7 @@ int launch_bound_from_slots(const float* slot_max, int B, int P, int slots, int 
     set_error("bound_from_slots: slots=%d kc=%d P=%d", slots, kc, P);
     return ICD_E_ARG;
   }
-  const int grid = (B + kMergeWarps - 1) / kMergeWarps;
-  bound_from_slots_kernel<<<grid, kMergeWarps * 32, 0, st>>>(slot_max, B, P, kc, bound_key_out);
+  bound_from_slots_kernel<<<B, kFolds * 32, 0, st>>>(slot_max, B, P, kc, bound_key_out);
   count_launch();
   ICD_CUDA(cudaGetLastError());
   return ICD_OK;
