@@ -18,6 +18,7 @@ search (on a 1 M-row check corpus gathered onto every rank) and an independent t
 
 Besides the headline (batch 1024: tensor-bound by arithmetic) the same resident table is measured at
 batch 128 (`hbm_point`, HBM-bound) and batch 256 (`ridge_point`), each over >= 1 s of load with its own clocks.
+`config1_point` (N = 1) is BASELINE configs[1]: 10 000 queries against a table of the reference's own 40 474 rows.
 The `encoder` object is BASELINE configs[2] (S = 64, B = 4096) plus `e2e_text`: EmbeddingService text in ->
 embeddings out over >= 200 k real ICD strings (native tokeniser, pinned staging, GPU encoder).
 
@@ -574,6 +575,59 @@ def bench_encoder_text(dev, rank, world, min_texts=200_000):
 
 
 # ---------------------------------------------------------------------------------------------- scan
+def bench_config1(torch, dev, native, VectorIndex, peaks, k=10, rows=40474, nq=10_000, steps=20):
+    """BASELINE configs[1]: exact top-10 of 10 000 queries against a table of the reference's own size (40 474 rows,
+    62 MB of bf16: L2-sized) with the level re-rank, one GPU.  `value` = queries/s with queries and results resident
+    (CUDA events over `steps` calls), `e2e` = the same call with numpy fp32 queries and numpy results (pageable host
+    memory, what MilvusService.search_batch hands over).  256 of the result rows are compared with an exact fp32
+    torch search."""
+    table, levels = make_corpus(torch, rows, dev, 4242)
+    q = make_queries(torch, nq, dev, seed=4243).float()   # fp32 in, as the service hands them over
+    idx = VectorIndex(DIM, device=dev.index)
+    idx.adopt(table, levels)
+    stream = torch.cuda.current_stream(dev)
+    o = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+         torch.empty((nq, k), dtype=torch.int64, device=dev))
+    run = lambda: idx.search(q, k, weight_mode=native.WEIGHT_RERANK, out=o, stream=stream.cuda_stream, sync=False)  # noqa: E731
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize(dev)
+    l0 = native.lib().icd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    launches = (native.lib().icd_launch_count() - l0) // steps
+    q_np = q.float().cpu().numpy()
+    for _ in range(2):
+        idx.search(q_np, k, weight_mode=native.WEIGHT_RERANK)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        hs, hr, hi = idx.search(q_np, k, weight_mode=native.WEIGHT_RERANK)
+    ms_e2e = (time.perf_counter() - t0) / steps * 1e3
+    # exact fp32 check of a sample (raw top-k as sets up to ties within 1e-6, re-rank order by weighted score)
+    sample = torch.arange(0, nq, nq // 256, device=dev)[:256]
+    exact = q[sample].float() @ table.float().T
+    ref_s, ref_i = exact.topk(k, dim=1)
+    got_i, got_r, got_s = o[2][sample], o[1][sample], o[0][sample]
+    kth = ref_s[:, -1:]
+    ok = bool(((got_r >= kth - 1e-6).all()) and (got_s[:, 1:] <= got_s[:, :-1]).all() and
+              torch.allclose(got_r, exact.gather(1, got_i), atol=2e-6) and
+              torch.equal(torch.from_numpy(hi).to(dev)[sample], got_i))
+    same = float((got_i.sort(dim=1).values == ref_i.sort(dim=1).values).all(dim=1).float().mean())
+    idx.close()
+    flops = 2.0 * nq * rows * DIM
+    return {"workload": f"exact top-{k} + level re-rank, {nq} queries x {rows} rows x {DIM} bf16 (BASELINE configs[1]), one call",
+            "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_call": ms, "steps": steps, "gpu_launches_per_call": int(launches),
+            "tflops": flops / (ms * 1e-3) / 1e12, "frac_of_bf16_sustained": flops / (ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_call": ms_e2e, "h2d_bytes_per_step": nq * DIM * 4,
+                    "d2h_bytes_per_step": nq * k * 16, "buffers": "numpy fp32 queries, numpy results (pageable)"},
+            "checks": {"sample_matches_exact_fp32": ok, "sample_rows_with_identical_id_sets": same, "sample": 256}}
+
+
 def scan_roofline(peaks, rows_local, B, k, scan_us, calls, kernel):
     flops = 2.0 * B * rows_local * DIM                     # per scan launch (per GPU)
     bytes_alg = rows_local * DIM * 2 + B * DIM * 2 + B * k * 16
@@ -826,6 +880,14 @@ def main():
             n_steps = max(5, int(math.ceil(1000.0 / max(probe["ms_per_step"], 1e-3))))
             points[name] = measure(pb, n_steps, 2, 1.0, with_e2e=False)
 
+    # ------------------------------------------------ BASELINE configs[1]: the reference's own table size (rank 0, N = 1)
+    config1 = None
+    if not args.no_points and world == 1:
+        try:
+            config1 = bench_config1(torch, dev, native, VectorIndex, peaks)
+        except Exception as e:  # auxiliary: the headline must still print
+            config1 = {"error": repr(e)[:300]}
+
     # ------------------------------------------------ encoder (BASELINE configs[2]), data-parallel replicas
     enc = None
     if not args.no_encoder:
@@ -887,6 +949,8 @@ def main():
                           "steps": pt["steps"], "n_gpus": world,
                           "roofline": scan_roofline(peaks, rows_local, pt["B"], k, pt["scan_us"], pt["calls"], pt["kernel"]),
                           "clocks": pt["clocks"], "gpu_launches": pt["launches"]}
+        if config1 is not None:
+            line["config1_point"] = config1
         if not args.no_cpu_baseline and world == 1:
             sample = CpuScanSample(args.cpu_rows, args.cpu_batch or B)
             sample.calibrate(5, 25.0)

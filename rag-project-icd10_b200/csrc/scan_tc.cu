@@ -215,32 +215,34 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     // row at chunk c ^ (row & 7)), the layout the SS MMA descriptor expects
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     const uint4* qrow = reinterpret_cast<const uint4*>(p.q + (size_t)query * p.dim);
-    for (int c16 = 0; c16 < p.dim / 32; ++c16) {  // 16 columns = 32 bf16 = 4 x uint4
-      uint32_t r[16];
-      if (query < p.B) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 t = qrow[c16 * 4 + v];
-          r[4 * v + 0] = t.x;
-          r[4 * v + 1] = t.y;
-          r[4 * v + 2] = t.z;
-          r[4 * v + 3] = t.w;
-        }
-      } else {
-#pragma unroll
-        for (int v = 0; v < 16; ++v) r[v] = 0u;
-      }
-      const int kb = c16 >> 1;  // 64 bf16 per K block = two 32-element halves
+    // two K blocks (2 x 64 bf16 = 16 x uint4 of this query's row) per step, the loads of a step issued before its
+    // stores: a step's L2 / HBM latency is paid once, not per 16 columns (r02t: ~10 us of every launch went here)
+    auto put = [&](int kb, const uint32_t* r) {
       if (kb < p.nkb_tmem) {
-        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(c16 * 16), r);
+        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(kb * 32), r);
+        ptx::tmem_st_32x32b_x16(lane_addr + (uint32_t)(kb * 32 + 16), r + 16);
       } else {
         unsigned char* row = q_tail + (size_t)(kb - p.nkb_tmem) * kQTileBytes + ep_lane * 128;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int chunk = (c16 & 1) * 4 + v;
-          *reinterpret_cast<uint4*>(row + ((chunk ^ (ep_lane & 7)) << 4)) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
-        }
+        for (int chunk = 0; chunk < 8; ++chunk)
+          *reinterpret_cast<uint4*>(row + ((chunk ^ (ep_lane & 7)) << 4)) =
+              make_uint4(r[4 * chunk], r[4 * chunk + 1], r[4 * chunk + 2], r[4 * chunk + 3]);
       }
+    };
+    for (int kb = 0; kb < p.nkb; kb += 2) {
+      uint32_t r[64];
+      const bool two = kb + 1 < p.nkb;
+#pragma unroll
+      for (int v = 0; v < 16; ++v) {
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (query < p.B && (v < 8 || two)) t = qrow[kb * 8 + v];
+        r[4 * v + 0] = t.x;
+        r[4 * v + 1] = t.y;
+        r[4 * v + 2] = t.z;
+        r[4 * v + 3] = t.w;
+      }
+      put(kb, r);
+      if (two) put(kb + 1, r + 32);
     }
     ptx::tmem_st_wait();
     ptx::fence_proxy_async_smem();  // the tail tiles are read by the tensor core (async proxy)
@@ -486,14 +488,17 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     int* gb = (p.gbound && live) ? p.gbound + query : nullptr;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
     int it = 0;
+    // the bound is read one tile ahead: its L2 round trip (~700 cycles) overlaps the previous tile's epilogue instead of
+    // standing in front of this one's (a bound that is one tile old is still a bound)
+    int key = (int)0x80808080;
+    if (gb) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(key) : "l"(gb));
     for (int64_t t = t0; t < t1; ++t, ++it) {
       if (gb) {
         // bound proven by any row group: rows strictly below it cannot reach the global top-k
         // (equal scores are still admitted: the id tie-break is decided at the merge)
-        int key;
-        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(key) : "l"(gb));
         const float bound = key_float(key);
         adm = fmaxf(thr, nextafterf(bound, -INFINITY));
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(key) : "l"(gb));
       }
       const int buf = (p.nacc == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nacc == 2) ? (uint32_t)(it >> 1) : (uint32_t)it;
