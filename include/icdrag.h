@@ -84,7 +84,9 @@ int icd_device_count(void);
  * split, 0 = all that fit), "scan_generic" (1 = the run-time-shaped MMA issue loop instead of the unrolled one), "scan_pre_slots"
  * (0 = the list-based sampling pre-pass instead of the slot-maxima one), "scan_small_pre" (0 = no pre-pass on tables
  * below 512 k rows), "enc_pdl" (0 = plain stream order between the
- * encoder's kernels instead of programmatic dependent launch).
+ * encoder's kernels instead of programmatic dependent launch), "enc_skinny" (forwards of few tokens -- batch-1
+ * encode_query -- run their linear layers as a weight stream over all SMs instead of tile GEMMs: 1 = up to 32 tokens
+ * (default), 0 = never, 2 = up to 64; the two paths agree to bf16 rounding).
  * Results never depend on them.  Production builds read NO environment variables on the compute path; profiling
  * builds (-DICD_PROFILING) additionally honour ICD_SCAN_*, ICD_GEMM_PAIR, ICD_ENC_FUSED_LN, ICD_ATTN_DBG. */
 int icd_tune(const char* key, int value);

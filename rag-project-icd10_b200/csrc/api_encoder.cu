@@ -387,7 +387,29 @@ static int encode_hidden(icd_encoder* e, const int32_t* ids, const int32_t* lens
                     : launch_attention_tc_long(e->m_qkv, d_lens, B, S, e->att_part, e->att_stats, e->ctx, st);
   };
   const void* final_h = e->h;
-  if (e->fused_ln) {
+  const bool skinny = e->fused_ln && M <= skinny_max_tokens() && skinny_linear_supported(M, H, H) &&
+                      skinny_linear_supported(M, 3 * H, H) && skinny_linear_supported(M, I, H) && skinny_linear_supported(M, H, I);
+  if (skinny) {
+    // A handful of tokens (batch-1 encode_query): the same deferred-LayerNorm dataflow as below, every linear layer
+    // as a weight stream over all SMs (skinny_linear.cu); the row statistics are computed by the consumer itself.
+    for (size_t l = 0; l < e->layers.size(); ++l) {
+      LayerW* L = e->layers[l];
+      const LayerW* P = l ? e->layers[l - 1] : nullptr;
+      SkinnyArgs g{};
+      g = SkinnyArgs{e->h, L->wqkv, L->bqkv, P ? L->cqkv : nullptr, nullptr, e->qkv, M, 3 * H, H, EPI_BIAS, P ? 1 : 0, eps};
+      ICD_TRY(launch_skinny_linear(g, st));
+      ICD_TRY(attention());
+      g = SkinnyArgs{e->ctx, L->wo, L->bo_r, P ? P->ln2g : nullptr, e->h, e->t, M, H, H, EPI_BIAS_RESIDUAL, 0, eps};
+      ICD_TRY(launch_skinny_linear(g, st));
+      g = SkinnyArgs{e->t, L->w1, L->b1, L->c1, nullptr, e->f, M, I, H, EPI_BIAS_GELU, 1, eps};
+      ICD_TRY(launch_skinny_linear(g, st));
+      g = SkinnyArgs{e->f, L->w2, L->b2_r, L->ln1g, e->t, e->h, M, H, I, EPI_BIAS_RESIDUAL, 0, eps};
+      ICD_TRY(launch_skinny_linear(g, st));
+    }
+    LayerW* L = e->layers.back();
+    ICD_TRY(launch_layernorm(e->h, M, L->ln2g, L->ln2b, eps, e->h1, st));
+    final_h = e->h1;
+  } else if (e->fused_ln) {
     // Deferred LayerNorm: e->h carries the layer input -- normalised for layer 0 (embed_ln), the un-normalised
     // FFN-down output x2 = LN1(x1) + FFN(LN1(x1)) afterwards -- and e->t the un-normalised x1 = LN2(x2') + attn;
     // stats2 / stats1 hold their row statistics.  No LayerNorm launch until the one that closes the last layer.

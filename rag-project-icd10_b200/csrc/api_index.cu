@@ -300,6 +300,10 @@ int icd_tune(const char* key, int value) {
     encoder_set_pdl(value);
     return ICD_OK;
   }
+  if (!strcmp(key, "enc_skinny")) {
+    encoder_set_skinny(value);
+    return ICD_OK;
+  }
   if (tensor_scan_tune(key, value) != ICD_OK) {
     set_error("icd_tune: unknown key '%s'", key);
     return ICD_E_ARG;

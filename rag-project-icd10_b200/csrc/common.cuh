@@ -93,4 +93,28 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   return r;
 }
 
+// ------------------------------------------------------------------ GELU of the encoder's FFN (gemm_tc.cu, skinny_linear.cu)
+// HF "gelu" = x * Phi(x) with Phi(x) = 0.5 * (1 + erf(x / sqrt(2))).  The epilogue of the FFN-up GEMM
+// (gemm_tc.cu) evaluates 32 K of these per 128 x 256 tile while the next tile's MMAs run (K = 768: the MMAs of a tile
+// take about as long as its epilogue), so every instruction counts.  Phi is evaluated as a logistic of an odd quintic
+// fitted to the erf form, written through tanh so that it costs ONE MUFU op:
+//   Phi(x) ~= 1 / (1 + exp(-2 u)) = 0.5 (1 + tanh(u)),  u = c x + a x^3 + b x^5
+//   gelu(x) ~= hx + hx tanh(u),  hx = x / 2
+// (c, a, b from a minimax fit: max |x Phi(x) - gelu_erf(x)| = 2.6e-5 with exact tanh; tanh.approx.f32 adds at most
+// 2^-11 |hx|, below the bf16 rounding of the stored value; tests/test_encoder_gpu.py checks the formula against
+// erf).  x^2 is clamped so the quintic stays monotone.  8 FP32 instructions, no branches.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  constexpr float kC = 7.97507884e-01f, kA = 3.70056460e-02f, kB = -3.51516788e-04f;
+  const float t = fminf(x * x, 36.0f);
+  float p = fmaf(kB, t, kA);
+  p = fmaf(p, t, kC);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(p * x), hx);
+}
+
 }  // namespace icd

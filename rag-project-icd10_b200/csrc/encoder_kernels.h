@@ -64,6 +64,28 @@ int gemm_make_map_a(void* map128, const void* base, int64_t rows, int K);
 int gemm_make_map_b(void* map128, const void* base, int64_t rows, int K);
 int gemm_make_map_out(void* map128, const void* base, int64_t rows, int N);
 
+// ---- skinny_linear.cu : the same linear layers for M <= 64 tokens (batch-1 encode_query) on every SM at once
+struct SkinnyArgs {
+  const void* A;       // [M, K] bf16
+  const void* W;       // [N, K] bf16
+  const float* bias;   // [N]
+  const float* vec2;   // [N]: c when lnin, gamma when the residual goes through a LayerNorm, else null
+  const void* res;     // [M, N] bf16 residual stream (EPI_BIAS_RESIDUAL) or null
+  void* out;           // [M, N] bf16
+  int M, N, K;
+  int epi;             // GemmEpilogue
+  int lnin;            // A is an un-normalised stream: LayerNorm folded into W / bias / vec2 (rows of 768)
+  float eps;
+};
+// 1 (default): forwards of at most 32 tokens take this path; icd_tune("enc_skinny", 0) sends them through the tile
+// kernels like every larger batch, 2 extends it to the 64 tokens the kernel supports.  Results agree to bf16 rounding
+// (different summation order).  skinny_max_tokens() = the current limit (0, 32 or 64).
+int encoder_skinny();
+void encoder_set_skinny(int mode);
+int skinny_max_tokens();
+bool skinny_linear_supported(int M, int N, int K);
+int launch_skinny_linear(const SkinnyArgs& a, cudaStream_t st);
+
 // ---- encoder_kernels.cu
 // h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0]); ids outside [0, vocab) read row `unk`
 int launch_embed_ln(const int32_t* ids, int M, int S, int vocab, int unk, const float* word, const float* pos,

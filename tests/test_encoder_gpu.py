@@ -101,6 +101,72 @@ def test_device_tensors_and_large_batch(small):
     assert cosine_rows(out.cpu().numpy(), ref).min() >= COS_MIN
 
 
+def _shifted_state(seed, layers, vocab):
+    """Residual streams whose per-row mean is several sigma from zero, LayerNorm gains / offsets far from (1, 0)."""
+    import torch
+    state = oenc.synthetic_state_dict(seed=seed, num_layers=layers, vocab_size=vocab)
+    g = torch.Generator().manual_seed(99)
+    for name in list(state):
+        if name.endswith("attention.output.dense.bias") or name.endswith("output.dense.bias"):
+            state[name] = state[name] + 3.0
+        elif name.endswith("LayerNorm.weight"):
+            state[name] = 0.25 + 2.0 * torch.rand(state[name].shape, generator=g)
+        elif name.endswith("LayerNorm.bias"):
+            state[name] = 1.5 * torch.randn(state[name].shape, generator=g)
+    return state
+
+
+@pytest.mark.parametrize("shifted", [False, True])
+def test_few_token_forwards_stream_the_weights_and_agree_with_the_tile_kernels(small, shifted):
+    """Forwards of few tokens (batch-1 encode_query, the reference's live pattern) run every linear layer as a weight
+    stream over all SMs (csrc/skinny_linear.cu) instead of 256 x 256 tensor-core tiles: up to 32 tokens by default,
+    up to the 64 the kernel supports with icd_tune enc_skinny = 2 (forced here so that its second pass is covered).
+    Same dataflow, same folded LayerNorms, different summation order: embeddings agree with the tile kernels'
+    (enc_skinny = 0) to bf16 rounding and both meet the oracle tolerance; 65 tokens take the tile path either way."""
+    N, E, W = _mods()
+    if shifted:
+        vocab, layers = 1500, 3
+        state = _shifted_state(21, layers, vocab)
+        cfg = N.BertCfg(vocab_size=vocab, hidden=768, layers=layers, heads=12, intermediate=3072, max_position=512,
+                        type_vocab=2, ln_eps=1e-12)
+        eng = E.EncoderEngine(cfg=cfg, blob=W.pack_state_dict(state, cfg), tokenizer=object(), device=0, max_tokens=8192)
+    else:
+        eng, state, layers, vocab = small
+    try:
+        rng = np.random.default_rng(77)
+        for B, S in ((1, 12), (1, 31), (1, 32), (1, 33), (2, 32), (1, 64), (4, 16), (3, 21), (7, 9), (1, 65), (5, 13)):
+            lens = rng.integers(1, S + 1, size=B).astype(np.int32)
+            lens[0] = S
+            ids = np.zeros((B, S), np.int32)
+            for b in range(B):
+                ids[b, :lens[b]] = rng.integers(1, vocab, size=lens[b])
+            try:
+                N.tune(enc_skinny=2)
+                l0 = N.lib().icd_launch_count()
+                got = eng.forward_ids(ids, lens)
+                launches = N.lib().icd_launch_count() - l0
+                hid = eng.read_hidden(B * S).reshape(B, S, 768)
+                N.tune(enc_skinny=0)
+                tile = eng.forward_ids(ids, lens)
+                hid_tile = eng.read_hidden(B * S).reshape(B, S, 768)
+            finally:
+                N.tune(enc_skinny=1)
+            auto = eng.forward_ids(ids, lens)                            # default: weight stream up to 32 tokens
+            assert np.array_equal(auto, got if B * S <= 32 else tile), (B, S)
+            assert launches == 1 + 5 * layers + 2                      # same launch count on either path
+            assert cosine_rows(got, tile).min() >= 0.9999, (B, S)
+            if B * S > 64:
+                assert np.array_equal(got, tile)                         # both calls took the tile kernels
+            ref, _, ref_h = _oracle_forward(state, layers, vocab, ids, lens)
+            assert cosine_rows(got, ref).min() >= COS_MIN, (B, S)
+            for b in range(B):
+                assert cosine_rows(hid[b, :lens[b]], hid_tile[b, :lens[b]]).min() >= 0.9995, (B, S, b)
+                assert cosine_rows(hid[b, :lens[b]], ref_h[b, :lens[b]]).min() >= 0.998, (B, S, b)
+    finally:
+        if shifted:
+            eng.close()
+
+
 def test_deferred_layernorm_with_shifted_and_scaled_streams():
     """The LayerNorms are folded into the GEMMs on either side of them (csrc/gemm_tc.cu: y = rs (x W'^T) - rs mu c + b').
     That identity cancels mu c against the accumulator, so it is exercised where it is least comfortable: residual
