@@ -33,6 +33,11 @@ struct icd_index {
   int map_gen = -1;
   // workspace
   icd::DeviceBuf q_f32, q_bf16, part_score, part_id, cand_score, cand_id, out_stage, in_stage, gbound;
+  // pipelined searches from host buffers (icd_index_search, large batches): the second set of query / result staging
+  // buffers, the copy stream and the events that order the two streams
+  icd::DeviceBuf q_f32_alt, q_bf16_alt, out_stage_alt;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};   // [set]: copied in / searched
   // stage timing (scan, merge, finalise): a ring of event quads so that back-to-back searches can be averaged
   // afterwards without a host sync between them (bench.py's roofline figure); ev = the quad of the current call
   static constexpr int kTimingRing = 64;

@@ -355,6 +355,34 @@ def test_small_table_pre_pass_is_a_performance_device(pkg, native, n, B, k, keep
             assert ids[b, 0] == n // 3 + 4 + b and ids[b, 1] == n - 4 + b, (b, ids[b, :3])
 
 
+@pytest.mark.parametrize("keep_f32", [False, True])
+def test_large_host_batches_are_pipelined_and_identical(pkg, native, keep_f32):
+    """Batches of >= 4096 queries handed over in host memory run in chunks of 2048 on two streams (copy-in of the next
+    chunk under the scan of the current one, two sets of staging buffers, copy-back one chunk behind): same results,
+    bit for bit, as the same queries in small calls and as one call with device-resident buffers; repeated calls and a
+    ragged last chunk included."""
+    import torch
+    n, dim, k = 40474, 768, 10
+    corpus = _corpus(n, dim, seed=301)
+    levels = _levels(n, seed=302)
+    idx = _index(pkg, corpus, levels, keep_f32=keep_f32)
+    for B in (4096, 4096 + 777, 10_000):
+        q = _corpus(B, dim, seed=303 + B)
+        small = [idx.search(q[lo:lo + 1000], k, weight_mode=native.WEIGHT_RERANK) for lo in range(0, B, 1000)]
+        want = [np.concatenate([p[i] for p in small]) for i in range(3)]
+        for _ in range(2):
+            got = idx.search(q, k, weight_mode=native.WEIGHT_RERANK)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), B
+        dev = idx.search(torch.from_numpy(q).cuda(), k, weight_mode=native.WEIGHT_RERANK)
+        for a, b in zip(dev, want):
+            assert np.array_equal(a.cpu().numpy(), b), B
+    ref_s, ref_i = osearch.exact_topk(corpus, q[:256], k)
+    s, r, i = idx.search(q, k, weight_mode=native.WEIGHT_NONE)
+    check_topk(i[:256], r[:256], ref_i, ref_s, _exact_of(corpus, q), score_tol=2e-6)
+    idx.close()
+
+
 def test_config1_10k_queries_against_the_icd_sized_corpus(pkg, native):
     """BASELINE.json configs[1]: batched exact top-10 of 10 000 synthetic diagnosis queries against a 40 474-row
     corpus (the size of data/ICD_10v601.csv) with the hierarchical level weights, one GPU.  Queries go through in
