@@ -84,6 +84,7 @@ int encoder_skinny();
 void encoder_set_skinny(int mode);
 int skinny_max_tokens();
 bool skinny_linear_supported(int M, int N, int K);
+int launch_skinny_linear(const SkinnyArgs& a, cudaStream_t st);
 
 // ---- encoder_kernels.cu
 // h0[M,768] = LayerNorm(word[ids] + pos[t] + type[0]); ids outside [0, vocab) read row `unk`
