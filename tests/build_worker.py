@@ -34,10 +34,17 @@ def main():
     lo, hi = col.row_lo, col.row_hi
     probes = ["急性胃肠炎", "霍乱", "伤寒", "结核性脑膜炎", "急性胃肠炎 发热"]
     sharded = [ms.search(es.encode_query(p), top_k=10) for p in probes]               # collective: every rank
-    batch = [list(c) for c in ms.search_batch(es.encode_queries(probes), top_k=10)]
+    # the batched call against single calls on the SAME vectors (a text encoded alone takes the few-token kernels, in a
+    # batch the tile kernels: equal to bf16 rounding, which may swap near-ties of these random-weight embeddings)
+    qv = es.encode_queries(probes)
+    batch = [list(c) for c in ms.search_batch(qv, top_k=10)]
+    one_by_one = [ms.search(qv[i], top_k=10) for i in range(len(probes))]
     res = {"ok": bool(ok), "n": n, "rows": [lo, hi], "resident": len(col.index)}
     good = ok and n == int(os.environ["ICD_TEST_ROWS"]) and len(col.index) == hi - lo
-    good = good and all([h["code"] for h in a] == [h["code"] for h in b] for a, b in zip(sharded, batch))
+    good = good and all([h["code"] for h in a] == [h["code"] for h in b] for a, b in zip(one_by_one, batch))
+    good = good and all(len({h["code"] for h in a} & {h["code"] for h in b}) >= 8 for a, b in zip(sharded, batch))
+    if not good:
+        print("rank", rank, "batched vs single searches differ", flush=True)
     # a fresh sharded service maps its slice back from the column files and answers identically
     ms2 = M.MilvusService(embedding_service=es)
     shard = importlib.import_module("rag-project-icd10_b200.engine.shard")
