@@ -85,8 +85,8 @@ int icd_device_count(void);
  * (0 = the list-based sampling pre-pass instead of the slot-maxima one), "scan_small_pre" (0 = no pre-pass on tables
  * below 512 k rows), "enc_pdl" (0 = plain stream order between the
  * encoder's kernels instead of programmatic dependent launch), "enc_skinny" (forwards of few tokens -- batch-1
- * encode_query -- run their linear layers as a weight stream over all SMs instead of tile GEMMs: 1 = up to 32 tokens
- * (default), 0 = never, 2 = up to 64; the two paths agree to bf16 rounding).
+ * encode_query -- run their linear layers as a weight stream over all SMs instead of tile GEMMs: 1 = up to 64 tokens
+ * (default), 0 = never; the two paths agree to bf16 rounding).
  * Results never depend on them.  Production builds read NO environment variables on the compute path; profiling
  * builds (-DICD_PROFILING) additionally honour ICD_SCAN_*, ICD_GEMM_PAIR, ICD_ENC_FUSED_LN, ICD_ATTN_DBG. */
 int icd_tune(const char* key, int value);

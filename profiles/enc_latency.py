@@ -7,7 +7,7 @@ import bench
 N = importlib.import_module("rag-project-icd10_b200._native")
 eng = bench.synthetic_engine(num_layers=12, device=0, max_tokens=8192)
 rng = np.random.default_rng(1)
-for S in (8, 12, 24, 48, 64, 65):
+for S in (8, 12, 16, 17, 24, 32, 48, 64, 65):
     ids = rng.integers(1000, 20000, size=(1, S)).astype(np.int32); lens = np.array([S], np.int32)
     d_ids = torch.from_numpy(ids).cuda(); d_lens = torch.from_numpy(lens).cuda()
     row = {"S": S}

@@ -2,7 +2,7 @@
 """Counts the Blackwell-specific SASS mnemonics per kernel of libicdrag.so (no GPU needed):
    python profiles/sass_evidence.py > profiles/sass_evidence.txt
 tcgen05.mma = UTC*MMA, tcgen05.ld / st = LDTM / STTM, TMA = UTMALDG / UTMASTG, tcgen05.commit = UTCBAR, mbarrier = SYNCS;
-HMMA is mma.sync: only in skinny_linear_kernel, the few-token (<= 32) latency path of the encoder, where a 128-lane
+HMMA is mma.sync: only in skinny_linear_kernel, the few-token (<= 64) latency path of the encoder, where a 128-lane
 tcgen05 tile would be 90 % padding; every throughput kernel is tcgen05."""
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -77,9 +77,9 @@ struct SkinnyArgs {
   int lnin;            // A is an un-normalised stream: LayerNorm folded into W / bias / vec2 (rows of 768)
   float eps;
 };
-// 1 (default): forwards of at most 32 tokens take this path; icd_tune("enc_skinny", 0) sends them through the tile
-// kernels like every larger batch, 2 extends it to the 64 tokens the kernel supports.  Results agree to bf16 rounding
-// (different summation order).  skinny_max_tokens() = the current limit (0, 32 or 64).
+// 1 (default): forwards of at most 64 tokens take this path; icd_tune("enc_skinny", 0) sends them through the tile
+// kernels like every larger batch (2 = everything the kernel supports: the same today).  Results agree to bf16 rounding
+// (different summation order).  skinny_max_tokens() = the current limit (0 or 64).
 int encoder_skinny();
 void encoder_set_skinny(int mode);
 int skinny_max_tokens();

@@ -2,13 +2,13 @@
 //
 // Replaces the same nn.Linear calls as gemm_tc.cu (reference call sites services/embedding_service.py:81,120 --
 // model.encode of ONE text, the reference's only live usage: multi_diagnosis_service.py:152-153) when the whole batch is
-// at most 32 tokens.  There the 256 x 256 tcgen05 tile is the wrong tool: a forward is 48 GEMM launches of ~11 us each
+// at most 64 tokens.  There the 256 x 256 tcgen05 tile is the wrong tool: a forward is 48 GEMM launches of ~11 us each
 // whatever the length (r02o: 0.70 ms device-side for 12 tokens), because 3 .. 12 CTA pairs walk all of K serially and
 // pull every weight through a handful of SMs (FFN-down: 3 pairs x 48 K blocks).  With so few rows the layer is a
 // weight STREAM (14 MB per layer, read once) in front of a dependency wait, so this kernel is built around that:
 //
-//   * a warp owns EIGHT output features and a K range of 256 or 768 elements, and holds that whole 8 x K slice of W in
-//     registers (<= 96 per thread), loaded BEFORE griddepcontrol.wait: weights are constants, so under programmatic
+//   * a warp owns EIGHT output features and a K range of 256 elements, and holds that whole 8 x 256 slice of W in
+//     registers (32 per thread), loaded BEFORE griddepcontrol.wait: weights are constants, so under programmatic
 //     dependent launch they stream in while the previous kernel is still finishing, and what is left after the wait
 //     is a few dozen L1 / L2 reads of activation rows and the same number of MMAs;
 //   * mma.sync m16n8k16 (bf16 x bf16 -> fp32; 16 tokens x 8 features): for 12 tokens there is nothing a 128-row
@@ -16,13 +16,17 @@
 //     from global memory as 16-byte pieces: lane (r, q) reads elements [8 q, 8 q + 8) of a 32-element K block of
 //     row r and uses them as the fragment pairs of TWO MMAs; the K order inside a block is permuted the same way for A
 //     and W, which a dot product does not see.  (A first version on fp32 FMAs cost 16 us per token and forward: r02y.)
-//   * K splits (KS warps per feature group: O and FFN-down, which have only 96 feature groups) meet in shared memory and
-//     are added in a fixed order (deterministic);
+//   * the K / 256 warps of a feature group (3, or 12 for FFN-down) meet in shared memory and are added in a fixed order
+//     (deterministic).  Short K ranges per warp are what keeps the activation loads deep: with 768 elements per warp
+//     the weight slice took 96 registers, the compiler kept 8 loads in flight, and since L1 holds sectors, not lines
+//     (ncu r02ah: 1.5 % L1 hits in the K-split kernels, prefetch.global.L1 notwithstanding) every 16-token tile cost
+//     six L2 round trips -- 3.7 us per tile and launch;
 //   * epilogue per (token, feature) as in gemm_tc.cu: bias, deferred-LayerNorm input correction, erf-GELU, residual
 //     through LayerNorm.  The row statistics the deferred LayerNorm needs are computed HERE from the rows themselves
 //     (<= 64 rows of 768), so this path neither reads nor writes the statistics buffers of the tile kernels.
 //
-// Grid: QKV 72 CTAs x 4 warps, FFN-up 96 x 4, O 96 x 3 (K split 3), FFN-down 96 x 4 (K split 4).
+// Grid per 32 tokens: QKV 72 CTAs x 12 warps (4 feature groups x 3 K ranges), FFN-up 96 x 12, O 96 x 3, FFN-down 96 x 12;
+// at most 16 tokens: 4 warps per CTA with 768 elements of K each (launch_skinny_linear).
 // Roofline: latency (a few microseconds per launch); the weight stream itself is ~2 us per layer at HBM speed.
 #include "common.cuh"
 #include "encoder_kernels.h"
@@ -33,7 +37,8 @@ namespace {
 
 constexpr int kH = 768;          // hidden size: the row length every LayerNorm statistic covers
 constexpr int kMaxTokens = 64;   // rows per launch (two passes of 32)
-constexpr int kMaxWarps = 4;
+constexpr int kMaxWarps = 12;
+constexpr int kBlk = 8;           // 32-element K blocks per warp: a K range of 256
 
 struct SkinnyParams {
   const __nv_bfloat16* A;    // [M, K]
@@ -61,11 +66,14 @@ __device__ __forceinline__ void mma16816(float* d, uint32_t a0, uint32_t a1, uin
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// EPI as in gemm_tc.cu; LNIN: A is an un-normalised stream (QKV of layers >= 1, FFN-up); NBLK: 32-element K blocks per warp
+// EPI as in gemm_tc.cu; LNIN: A is an un-normalised stream (QKV of layers >= 1, FFN-up); NBLK: 32-element K blocks per warp.
+// blockIdx.y = which 32 tokens: a second pass runs on other SMs instead of after the first (one after the other, each pass
+// cost its own chain of load -> MMA -> shared-memory sum -> residual load -> store, ~2.8 us per launch: r02ai)
 template <int EPI, bool LNIN, int NBLK>
-__global__ void __launch_bounds__(32 * kMaxWarps)
+__global__ void __launch_bounds__(32 * kMaxWarps, 1)
 skinny_linear_kernel(const SkinnyParams p) {
-  __shared__ float s_rs[kMaxTokens], s_nmr[kMaxTokens];   // LayerNorm of a row: y = x * rs + nmr
+  __shared__ float s_rs[32], s_nmr[32];                    // LayerNorm of a row of this CTA's 32: y = x * rs + nmr
+  const int m0 = (int)blockIdx.y * 32;
   __shared__ float s_part[kMaxWarps][2][4][32];            // K-split partial sums [warp][tile][fragment register][lane]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int r = lane >> 2, q = lane & 3;                   // fragment coordinates: row group, thread in group
@@ -90,14 +98,6 @@ skinny_linear_kernel(const SkinnyParams p) {
   ptx::griddep_launch();
   ptx::griddep_wait();
 
-  // pull the activation rows into L1 in one sweep (every warp of the CTA reads all M rows; left to the MMA loop, whose
-  // loads run 4 K blocks ahead, the first touch cost one L2 round trip per 4 blocks and 16-token tile: r02ab)
-  for (int i = threadIdx.x; i < p.M * (p.K / 64); i += blockDim.x)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.A + (size_t)(i / (p.K / 64)) * p.K + (i % (p.K / 64)) * 64));
-  if (with_res && p.vec2 != nullptr)   // ... and the residual rows the statistics below are taken over
-    for (int i = threadIdx.x; i < p.M * (kH / 64); i += blockDim.x)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p.res + (size_t)i * 64));
-
   // row statistics of the stream that goes through a LayerNorm here: A (LNIN) or the residual (vec2 given)
   const bool res_ln = with_res && p.vec2 != nullptr;
   if (LNIN || res_ln) {
@@ -106,7 +106,8 @@ skinny_linear_kernel(const SkinnyParams p) {
     // and 16 us at 64: r02aa)
     const __nv_bfloat16* src = LNIN ? p.A : p.res;   // both have rows of kH elements in that case
     const int sub = lane & 7, slot = lane >> 3;
-    for (int mb = 0; mb < p.M; mb += 4 * nwarps) {
+    const int m_end = min(p.M, m0 + 32);
+    for (int mb = m0; mb < m_end; mb += 4 * nwarps) {
       const int m = mb + 4 * warp + slot;
       const __nv_bfloat16* row = src + (size_t)min(m, p.M - 1) * kH + sub * 8;
       uint4 v[kH / 64];
@@ -128,17 +129,17 @@ skinny_linear_kernel(const SkinnyParams p) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
         ss += __shfl_xor_sync(0xffffffffu, ss, off);
       }
-      if (sub == 0 && m < p.M) {
+      if (sub == 0 && m < m_end) {
         const float mu = s * (1.0f / kH);
         const float rs = rsqrtf(fmaxf(fmaf(-mu, mu, ss * (1.0f / kH)), 0.0f) + p.eps);
-        s_rs[m] = rs;
-        s_nmr[m] = -mu * rs;
+        s_rs[m - m0] = rs;
+        s_nmr[m - m0] = -mu * rs;
       }
     }
   }
   __syncthreads();
 
-  for (int m0 = 0; m0 < p.M; m0 += 32) {
+  {
     // two tiles of 16 tokens; rows past M re-read row M - 1 (their results are never stored)
     // two accumulator sets per tile (the two MMAs of a K block): half the length of the dependent MMA chain
     float acc[2][4], acc2[2][4];
@@ -177,7 +178,6 @@ skinny_linear_kernel(const SkinnyParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[t][i] += acc2[t][i];
     if (p.ks > 1) {
-      if (m0) __syncthreads();   // the previous pass's partials have been consumed
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -203,7 +203,7 @@ skinny_linear_kernel(const SkinnyParams p) {
           const int m = m0 + 16 * t + r + 8 * h;
           if (m < p.M) {
             float rs = 1.0f, nmr = 0.0f;
-            if (LNIN || res_ln) rs = s_rs[m], nmr = s_nmr[m];
+            if (LNIN || res_ln) rs = s_rs[m - m0], nmr = s_nmr[m - m0];
             float o[2];
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
@@ -225,24 +225,24 @@ skinny_linear_kernel(const SkinnyParams p) {
 
 template <int EPI, bool LNIN, int NBLK>
 int launch_variant(const SkinnyParams& p, cudaStream_t st) {
-  ICD_CUDA(launch_chained(skinny_linear_kernel<EPI, LNIN, NBLK>, dim3(p.N / (8 * p.fw)), dim3(32 * p.ks * p.fw), 0, st, 1, p));
+  ICD_CUDA(launch_chained(skinny_linear_kernel<EPI, LNIN, NBLK>, dim3(p.N / (8 * p.fw), (p.M + 31) / 32), dim3(32 * p.ks * p.fw), 0, st,
+                          1, p));
   count_launch();
   return ICD_OK;
 }
 
 }  // namespace
 
-// 0 = never, 1 = forwards of at most kAutoTokens tokens (one pass of two 16-token tiles; measured on a B200, r02ac, 12
-// layers, device time per forward: 8 tokens 0.33 ms, 12: 0.34, 24: 0.49 against 0.71 for the tile kernels at any
-// length; 48 tokens = two passes: 0.71, break-even), 2 = everything the kernel supports (<= 64 tokens; tests)
-constexpr int kAutoTokens = 32;
+// 0 = never, 1 = forwards of at most kAutoTokens tokens, 2 = everything the kernel supports (the same 64 today; tests)
+constexpr int kAutoTokens = 64;
 static int g_encoder_skinny = 1;
 int encoder_skinny() { return g_encoder_skinny; }
 void encoder_set_skinny(int mode) { g_encoder_skinny = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 int skinny_max_tokens() { return g_encoder_skinny == 2 ? kMaxTokens : (g_encoder_skinny == 1 ? kAutoTokens : 0); }
 
 bool skinny_linear_supported(int M, int N, int K) {
-  return M >= 1 && M <= kMaxTokens && (K == 768 || K == 3072) && N % 32 == 0;
+  return M >= 1 && M <= kMaxTokens && (K == 768 || K == 3072) && N % 32 == 0 &&
+         (K / (32 * kBlk)) * (N > kH ? 4 : 1) <= kMaxWarps;
 }
 
 int launch_skinny_linear(const SkinnyArgs& a, cudaStream_t st) {
@@ -264,24 +264,27 @@ int launch_skinny_linear(const SkinnyArgs& a, cudaStream_t st) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a.out);
   p.M = a.M, p.N = a.N, p.K = a.K;
   p.eps = a.eps;
-  // shape of a CTA: wide outputs (QKV, FFN-up) -> four feature groups of 8 per CTA, each over all of K (24 blocks);
-  // 768 outputs -> one group per CTA (96 CTAs) with K split over its warps: 3 x 8 blocks (K = 768), 4 x 24 (K = 3072)
-  if (a.N > kH) {
-    p.ks = 1, p.fw = 4;
-  } else {
-    p.ks = a.K == kH ? 3 : 4, p.fw = 1;
-  }
-  const int nblk = a.K / 32 / p.ks;   // 24, 8 or 24
-  switch (a.epi) {
-    case EPI_BIAS:
-      if (nblk != 24) break;
-      return lnin ? launch_variant<EPI_BIAS, true, 24>(p, st) : launch_variant<EPI_BIAS, false, 24>(p, st);
-    case EPI_BIAS_GELU:
-      if (nblk != 24 || !lnin) break;
-      return launch_variant<EPI_BIAS_GELU, true, 24>(p, st);
-    case EPI_BIAS_RESIDUAL:
-      if (lnin) break;
-      return nblk == 8 ? launch_variant<EPI_BIAS_RESIDUAL, false, 8>(p, st) : launch_variant<EPI_BIAS_RESIDUAL, false, 24>(p, st);
+  // shape of a CTA.  More than 16 tokens: K / 256 warps per feature group of 8 (short K ranges keep a tile's activation
+  // loads all in flight); wide outputs (QKV, FFN-up) take four groups per CTA (12 warps, 72 / 96 CTAs per 32 tokens),
+  // 768 outputs one (O: 3 warps, FFN-down: 12; 96 CTAs).  Up to 16 tokens (one tile): one warp per group over 768
+  // elements of K (4 warps per CTA, FFN-down 4 K ranges) -- fewer partial sums to meet in shared memory; measured 0.337 vs
+  // 0.364 ms per 12-token forward (r02ac / r02ai), and the other way round from 24 tokens on (0.49 vs 0.43).
+  const bool one_tile = a.M <= 16;
+  const int nblk = (one_tile && !(a.N == kH && a.K == kH)) ? 24 : kBlk;
+  p.ks = a.K / (32 * nblk);
+  p.fw = a.N > kH ? 4 : 1;
+  if (p.ks * p.fw <= kMaxWarps) {
+    switch (a.epi) {
+      case EPI_BIAS:
+        if (nblk == 24) return lnin ? launch_variant<EPI_BIAS, true, 24>(p, st) : launch_variant<EPI_BIAS, false, 24>(p, st);
+        return lnin ? launch_variant<EPI_BIAS, true, kBlk>(p, st) : launch_variant<EPI_BIAS, false, kBlk>(p, st);
+      case EPI_BIAS_GELU:
+        if (!lnin) break;
+        return nblk == 24 ? launch_variant<EPI_BIAS_GELU, true, 24>(p, st) : launch_variant<EPI_BIAS_GELU, true, kBlk>(p, st);
+      case EPI_BIAS_RESIDUAL:
+        if (lnin) break;
+        return nblk == 24 ? launch_variant<EPI_BIAS_RESIDUAL, false, 24>(p, st) : launch_variant<EPI_BIAS_RESIDUAL, false, kBlk>(p, st);
+    }
   }
   set_error("skinny_linear: no kernel for epilogue %d (lnin %d) at N=%d K=%d", a.epi, a.lnin, a.N, a.K);
   return ICD_E_UNSUPPORTED;

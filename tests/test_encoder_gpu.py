@@ -119,8 +119,8 @@ def _shifted_state(seed, layers, vocab):
 @pytest.mark.parametrize("shifted", [False, True])
 def test_few_token_forwards_stream_the_weights_and_agree_with_the_tile_kernels(small, shifted):
     """Forwards of few tokens (batch-1 encode_query, the reference's live pattern) run every linear layer as a weight
-    stream over all SMs (csrc/skinny_linear.cu) instead of 256 x 256 tensor-core tiles: up to 32 tokens by default,
-    up to the 64 the kernel supports with icd_tune enc_skinny = 2 (forced here so that its second pass is covered).
+    stream over all SMs (csrc/skinny_linear.cu) instead of 256 x 256 tensor-core tiles: up to 64 tokens (two groups of
+    CTAs of 32 tokens each; one 16-token tile, two tiles and both groups are covered here).
     Same dataflow, same folded LayerNorms, different summation order: embeddings agree with the tile kernels'
     (enc_skinny = 0) to bf16 rounding and both meet the oracle tolerance; 65 tokens take the tile path either way."""
     N, E, W = _mods()
@@ -151,8 +151,8 @@ def test_few_token_forwards_stream_the_weights_and_agree_with_the_tile_kernels(s
                 hid_tile = eng.read_hidden(B * S).reshape(B, S, 768)
             finally:
                 N.tune(enc_skinny=1)
-            auto = eng.forward_ids(ids, lens)                            # default: weight stream up to 32 tokens
-            assert np.array_equal(auto, got if B * S <= 32 else tile), (B, S)
+            auto = eng.forward_ids(ids, lens)                            # default: weight stream up to 64 tokens
+            assert np.array_equal(auto, got if B * S <= 64 else tile), (B, S)
             assert launches == 1 + 5 * layers + 2                      # same launch count on either path
             assert cosine_rows(got, tile).min() >= 0.9999, (B, S)
             if B * S > 64:
