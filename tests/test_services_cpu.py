@@ -162,3 +162,52 @@ def test_header_is_plain_c_and_matches_the_library(tmp_path):
     assert out.returncode == 0, out.stderr
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and run.stdout.split()[0] == str(len(names)), (run.stdout, run.stderr)
+
+
+def test_lazy_batch_is_a_read_only_sequence_of_candidate_lists():
+    """MilvusService.search_batch hands back a LazyBatch: element b behaves like the list search() returns for query b,
+    built on access from the [B, k] result arrays (missing hits are -1 at the tail of a row)."""
+    import numpy as np
+    ms = importlib.import_module("rag-project-icd10_b200.services.milvus_service")
+
+    class _Svc:                                     # stands where MilvusService stands: one dict per (row, distance)
+        calls = 0
+
+        def _candidate_of_row(self, row_id, distance):
+            _Svc.calls += 1
+            return {"code": f"R{row_id}", "original_score": distance}
+
+    ids = np.array([[5, 3, 9], [7, -1, -1], [-1, -1, -1]], np.int64)
+    raw = np.array([[0.9, 0.8, 0.7], [0.5, 0.0, 0.0], [0.0, 0.0, 0.0]], np.float32)
+    batch = ms.LazyBatch(_Svc(), raw, ids)
+    assert len(batch) == 3 and _Svc.calls == 0                       # nothing is materialised up front
+    assert [len(c) for c in batch] == [3, 1, 0]
+    assert [h["code"] for h in batch[0]] == ["R5", "R3", "R9"] and _Svc.calls == 3
+    assert batch[0][1] == {"code": "R3", "original_score": float(np.float32(0.8))} and _Svc.calls == 3   # cached
+    assert batch[-2] == [{"code": "R7", "original_score": 0.5}] and list(batch[2]) == []
+    assert [len(c) for c in batch[1:]] == [1, 0] and batch[0] is batch[0]
+    assert batch == [list(c) for c in batch] and batch.row_ids is ids and batch.raw_scores is raw
+    assert list(batch[0].row_ids) == [5, 3, 9] and list(batch[1].raw_scores) == [0.5]
+    with pytest.raises(IndexError):
+        batch[3]
+    # the per-query object alone (what search_batch returned before): trims the tail itself
+    one = ms.LazyCandidates(_Svc(), raw[1], ids[1])
+    assert len(one) == 1 and one == [{"code": "R7", "original_score": 0.5}] and one[-1]["code"] == "R7"
+
+
+def test_every_documented_knob_is_accepted_and_unknown_ones_are_not(native):
+    """icd_tune is host state only (no GPU needed): every key include/icdrag.h documents is accepted, anything else is an
+    argument error with a message; the defaults are restored afterwards."""
+    hdr = open(os.path.join(ROOT, "include", "icdrag.h")).read()
+    doc = hdr[hdr.index("process-wide tuning knobs"):hdr.index("int icd_tune(")]
+    keys = sorted(set(re.findall(r'"((?:scan|enc)_[a-z_]+)"', doc)))
+    defaults = dict(scan_sample=-1, scan_drift=4, scan_tmax=16, scan_kbs=3, scan_kbs_pair=6, scan_pair=-1, scan_qsplit=-1,
+                    scan_qtmem=0, scan_generic=0, scan_pre_slots=1, scan_small_pre=1, enc_pdl=1, enc_skinny=1)
+    assert keys == sorted(defaults), (keys, sorted(defaults))
+    try:
+        for k in keys:
+            native.tune(**{k: 0})
+    finally:
+        native.tune(**defaults)
+    with pytest.raises(native.NativeError, match="unknown key"):
+        native.tune(scan_no_such_knob=1)
