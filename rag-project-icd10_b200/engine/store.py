@@ -95,6 +95,7 @@ class _Column:
     def __init__(self, path: Optional[str], dtype, width: int = 1):
         self.path, self.dtype, self.width = path, np.dtype(dtype), int(width)
         self.count = 0                      # committed elements (rows * width)
+        self._pending = 0                   # elements written so far (committed + the uncommitted tail)
         self._mem: List[np.ndarray] = []    # non-persistent stores keep the pieces here
         self._map: Optional[np.ndarray] = None
         self._mm = None
@@ -106,7 +107,7 @@ class _Column:
 
     def open(self, committed: int) -> None:
         """Bring the file to exactly `committed` elements (a longer file is the tail of a torn append)."""
-        self.count = int(committed)
+        self.count = self._pending = int(committed)
         if self.path is None:
             return
         want = self.count * self.item_bytes
@@ -175,7 +176,7 @@ class _Column:
                 os.fsync(fh.fileno())
 
     def commit(self) -> None:
-        self.count = getattr(self, "_pending", self.count)
+        self.count = self._pending
         if self.path is None:
             if len(self._mem) > 1:
                 self._mem = [np.concatenate(self._mem)]
